@@ -1,0 +1,66 @@
+"""ctypes binding of liblwm_b200.so (the C ABI declared in include/lwm_b200.h).
+
+The library is built in-tree by `__graft_entry__.build()`. A missing library is a hard error:
+there is deliberately no eager/PyTorch fallback for any op."""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "liblwm_b200.so")
+_lib = None
+
+c_void_p, c_int, c_ll, c_float = ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_float
+
+# name -> argtypes ; every function returns int status except where noted
+_SIGNATURES = {
+    "lwm_abi_version": [],
+    "lwm_attn_fwd_step": [c_void_p] * 8 + [c_int] * 5 + [c_ll, c_ll, c_int, c_void_p, c_ll, c_void_p, c_ll,
+                                                       c_float, c_int, c_int, c_void_p],
+    "lwm_attn_bwd_prep": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
+    "lwm_attn_bwd_step": [c_void_p] * 9 + [c_int] * 5 + [c_ll, c_ll, c_int, c_void_p, c_ll, c_void_p, c_ll,
+                                                       c_float, c_void_p],
+    "lwm_cast_f32_to_bf16": [c_void_p, c_void_p, c_ll, c_void_p],
+}
+
+
+class LwmError(RuntimeError):
+    pass
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise LwmError(
+            "liblwm_b200.so not found at %s — run `python __graft_entry__.py` (nvcc, sm_100a) first; "
+            "lwm_b200 has no CPU/PyTorch fallback" % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    lib.lwm_last_error.restype = ctypes.c_char_p
+    lib.lwm_last_error.argtypes = []
+    for name, argtypes in _SIGNATURES.items():
+        fn = getattr(lib, name, None)
+        if fn is None:
+            continue  # exported-symbol coverage is asserted by tests/test_abi.py
+        fn.restype = c_int
+        fn.argtypes = argtypes
+    _lib = lib
+    return lib
+
+
+def call(name, *args):
+    lib = load()
+    status = getattr(lib, name)(*args)
+    if status != 0:
+        raise LwmError("%s failed (status %d): %s" % (name, status, lib.lwm_last_error().decode()))
+
+
+def ptr(t):
+    """Device pointer of a torch tensor (None -> NULL)."""
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def stream_ptr(stream=None):
+    import torch
+    s = stream if stream is not None else torch.cuda.current_stream()
+    return ctypes.c_void_p(s.cuda_stream)

@@ -1,0 +1,71 @@
+// Small HBM-bound helpers around the attention tile kernels:
+//   lwm_attn_bwd_prep     delta[b,h,s] = sum_d dout*out  (the rowsum(g∘out) term of the reference's
+//                         custom_vjp bwd, SURVEY.md Appendix A `bwd`)
+//   lwm_cast_f32_to_bf16  final cast of the fp32 gradient accumulators to the input dtype
+#include "attn_common.cuh"
+#include "capi_internal.h"
+
+namespace lwm {
+
+// one warp per (b, s, h) row of 128 elements: 4 bf16 per lane from each tensor (8-byte loads)
+__global__ void bwd_prep_kernel(const __nv_bfloat16* __restrict__ out, const __nv_bfloat16* __restrict__ dout,
+                                float* __restrict__ delta, int B, int H, int S) {
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);  // over B*S*H
+  const long long n_rows = (long long)B * S * H;
+  if (row >= n_rows) return;
+  const int lane = threadIdx.x & 31;
+  const uint2 a = reinterpret_cast<const uint2*>(out + row * kHeadDim)[lane];
+  const uint2 g = reinterpret_cast<const uint2*>(dout + row * kHeadDim)[lane];
+  const __nv_bfloat162 a0 = *reinterpret_cast<const __nv_bfloat162*>(&a.x);
+  const __nv_bfloat162 a1 = *reinterpret_cast<const __nv_bfloat162*>(&a.y);
+  const __nv_bfloat162 g0 = *reinterpret_cast<const __nv_bfloat162*>(&g.x);
+  const __nv_bfloat162 g1 = *reinterpret_cast<const __nv_bfloat162*>(&g.y);
+  float acc = __low2float(a0) * __low2float(g0) + __high2float(a0) * __high2float(g0) +
+              __low2float(a1) * __low2float(g1) + __high2float(a1) * __high2float(g1);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) {
+    const int h = int(row % H);
+    const long long bs = row / H;
+    const int s = int(bs % S);
+    const int b = int(bs / S);
+    delta[((long long)b * H + h) * S + s] = acc;
+  }
+}
+
+__global__ void cast_f32_bf16_kernel(const float4* __restrict__ src, uint2* __restrict__ dst, long long n4) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
+       i += (long long)gridDim.x * blockDim.x) {
+    const float4 f = src[i];
+    dst[i] = make_uint2(pack_bf16x2(f.x, f.y), pack_bf16x2(f.z, f.w));
+  }
+}
+
+}  // namespace lwm
+
+using namespace lwm;
+
+extern "C" int lwm_attn_bwd_prep(const void* out, const void* dout, float* delta, int B, int H, int Sq, int D,
+                                 void* stream) {
+  if (!lwm_check_device()) return LWM_ERR_DEVICE;
+  if (D != kHeadDim) return lwm_fail(LWM_ERR_SHAPE, "attn_bwd_prep: head_dim must be 128");
+  if (!out || !dout || !delta) return lwm_fail(LWM_ERR_ARG, "attn_bwd_prep: null pointer");
+  const long long rows = (long long)B * Sq * H;
+  const int warps = 8;
+  bwd_prep_kernel<<<unsigned((rows + warps - 1) / warps), warps * 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(out), reinterpret_cast<const __nv_bfloat16*>(dout), delta, B, H, Sq);
+  return lwm_check_launch("bwd_prep_kernel");
+}
+
+extern "C" int lwm_cast_f32_to_bf16(const float* src, void* dst, long long n, void* stream) {
+  if (!lwm_check_device()) return LWM_ERR_DEVICE;
+  if (n % 4) return lwm_fail(LWM_ERR_SHAPE, "cast_f32_to_bf16: n must be a multiple of 4");
+  if (n == 0) return LWM_OK;
+  const long long n4 = n / 4;
+  const int threads = 256;
+  const long long want = (n4 + threads - 1) / threads;
+  const unsigned blocks = unsigned(want < 148LL * 16 ? want : 148LL * 16);
+  cast_f32_bf16_kernel<<<blocks, threads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const float4*>(src), reinterpret_cast<uint2*>(dst), n4);
+  return lwm_check_launch("cast_f32_bf16_kernel");
+}

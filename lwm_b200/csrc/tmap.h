@@ -1,0 +1,47 @@
+// Host-side TMA tensor-map construction. The driver entry point is resolved at run time through
+// the CUDA runtime (cudaGetDriverEntryPoint) so the library has no link-time dependency on libcuda.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace lwm {
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                    CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                    CUtensorMapFloatOOBfill);
+
+inline PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(p);
+  }
+  return fn;
+}
+
+// dims[rank] (innermost first), strides_bytes[rank-1] (for dims 1..rank-1), box[rank].
+inline bool encode_tmap(CUtensorMap* out, CUtensorMapDataType dt, int rank, const void* base,
+                        const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box,
+                        CUtensorMapSwizzle swz) {
+  PFN_encodeTiled fn = get_encode_fn();
+  if (!fn) return false;
+  cuuint64_t d[5], s[4];
+  cuuint32_t b[5], es[5];
+  for (int i = 0; i < rank; ++i) {
+    d[i] = dims[i];
+    b[i] = box[i];
+    es[i] = 1;
+  }
+  for (int i = 0; i < rank - 1; ++i) s[i] = strides_bytes[i];
+  CUresult r = fn(out, dt, static_cast<cuuint32_t>(rank), const_cast<void*>(base), d, s, b, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+}  // namespace lwm

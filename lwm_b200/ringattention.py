@@ -1,0 +1,191 @@
+"""Host side of the B200 RingAttention operator — same call signature as the reference's
+`ringattention(q, k, v, attn_bias, segment_ids, *, axis_name, float32_logits, cache_idx,
+blockwise_kwargs)` bound with functools.partial at lwm/llama.py:540-557 and called at
+lwm/llama.py:569 on per-device shards inside shard_map.
+
+Translation of the execution model:
+  * shard_map over mesh axis 'sp'  ->  one process per GPU; `axis_name` resolves to a
+    torch.distributed process group registered with `set_axis_group` (default: WORLD; a
+    non-initialised process group means ring size 1).
+  * lax.ppermute(k, v : i -> i+1)  ->  NCCL send/recv (batch_isend_irecv) on a side stream into
+    the other half of a double buffer while the tile kernel consumes the current half.
+  * the (numerator, denominator, max) scan carry -> fp32 carry buffers merged in the kernel's
+    epilogue (include/lwm_b200.h: lwm_attn_fwd_step).
+
+Everything numeric happens in liblwm_b200.so; this file only sequences launches and NCCL calls.
+There is no fallback: without the library / an sm_100 GPU the op raises.
+"""
+import math
+from typing import Optional
+
+import torch
+import torch.distributed as dist
+
+from . import _lib
+from . import ring_schedule as rs
+
+_AXIS_GROUPS = {}
+
+
+def set_axis_group(axis_name: str, group) -> None:
+    """Bind a mesh-axis name (the reference's 'sp') to a torch.distributed process group."""
+    _AXIS_GROUPS[axis_name] = group
+
+
+def _resolve_group(axis_name):
+    if not (dist.is_available() and dist.is_initialized()):
+        return None, 0, 1
+    group = _AXIS_GROUPS.get(axis_name, dist.group.WORLD)
+    return group, dist.get_rank(group), dist.get_world_size(group)
+
+
+def _check_blockwise_kwargs(kw, s_q, s_k):
+    kw = dict(kw or {})
+    cbs = kw.get("causal_block_size", None)
+    if cbs not in (None, 1):
+        raise NotImplementedError("causal_block_size must be None or 1 (lwm/llama.py:546 uses 1)")
+    if not kw.get("deterministic", True) and float(kw.get("attn_pdrop", 0.0)) > 0.0:
+        raise NotImplementedError("attention dropout is not supported (attn_pdrop is 0.0 in every LWM config)")
+    for name, s in (("query_chunk_size", s_q), ("key_chunk_size", s_k)):
+        c = kw.get(name)
+        if c is not None and s % int(c) != 0 and s > int(c):
+            raise ValueError("%s=%d must divide the per-device sequence length %d" % (name, c, s))
+    # policy / precision / prevent_cse / dropout_rng / dtype are XLA-side knobs: accepted, unused.
+    return cbs is not None
+
+
+def _prep_bias(attn_bias, B):
+    if attn_bias is None:
+        return None
+    b = attn_bias
+    if b.dim() == 4:
+        if b.shape[1] != 1 or b.shape[2] != 1:
+            raise ValueError("attn_bias must be [B,1,1,S_global] (lwm/llama.py:527,563)")
+        b = b.reshape(b.shape[0], b.shape[-1])
+    if b.shape[0] != B:
+        b = b.expand(B, b.shape[-1])
+    return b.to(torch.float32).contiguous()
+
+
+class _RingAttnFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, q, k, v, bias, seg, causal, axis_name, layout):
+        group, rank, world = _resolve_group(axis_name)
+        out, lse = ring_forward(q, k, v, bias, seg, causal, group, rank, world, layout)
+        ctx.save_for_backward(q, k, v, out, lse, bias, seg)
+        ctx.causal, ctx.axis_name, ctx.layout = causal, axis_name, layout
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        q, k, v, out, lse, bias, seg = ctx.saved_tensors
+        group, rank, world = _resolve_group(ctx.axis_name)
+        dq, dk, dv = ring_backward(q, k, v, out, lse, dout.contiguous(), bias, seg, ctx.causal, group, rank,
+                                   world, ctx.layout)
+        return dq, dk, dv, None, None, None, None, None
+
+
+def ringattention(q, k, v, attn_bias=None, segment_ids=None, *, axis_name="sp", float32_logits=True,
+                  cache_idx=None, blockwise_kwargs=None, layout="auto"):
+    """Drop-in for the reference op. q [B,Sq_loc,H,D], k/v [B,Sk_loc,H,D] bf16 CUDA shards of the
+    contiguously sequence-sharded tensors (in_specs lwm/llama.py:559-565); attn_bias
+    [B,1,1,S_global] additive (0 / finfo.min), segment_ids [B,S_global] or None, both replicated
+    along the ring. Returns the local output shard [B,Sq_loc,H,D]; differentiable w.r.t. q,k,v.
+
+    float32_logits: logits/softmax/carries are always fp32 here (the reference default, True).
+    layout: 'contiguous' = the reference's schedule; 'zigzag' = internally rebalance the causal
+    work across ranks (same inputs/outputs); 'auto' picks zigzag when it applies."""
+    if cache_idx is not None:
+        raise NotImplementedError("cache_idx is always None at the reference call site (lwm/llama.py:544)")
+    if not q.is_cuda:
+        raise _lib.LwmError("ringattention: tensors must live on an sm_100 GPU (no CPU fallback)")
+    if q.dtype != torch.bfloat16 or k.dtype != torch.bfloat16 or v.dtype != torch.bfloat16:
+        raise TypeError("ringattention: q, k, v must be bfloat16 (fp32 logits and accumulation are internal)")
+    B, Sq, H, D = q.shape
+    causal = _check_blockwise_kwargs(blockwise_kwargs, Sq, k.shape[1])
+    bias = _prep_bias(attn_bias, B)
+    seg = None
+    if segment_ids is not None:
+        seg = segment_ids.to(torch.int32).contiguous()
+    return _RingAttnFn.apply(q.contiguous(), k.contiguous(), v.contiguous(), bias, seg, causal, axis_name, layout)
+
+
+# ------------------------------------------------------------------------------------------------
+# single-step wrappers over the C ABI
+# ------------------------------------------------------------------------------------------------
+def fwd_step(q, k, v, out, lse, acc_o, acc_m, acc_l, q_pos0, k_pos0, causal, bias, seg, first, last,
+             stream=None):
+    B, Sq, H, D = q.shape
+    Sk = k.shape[1]
+    _lib.call("lwm_attn_fwd_step", _lib.ptr(q), _lib.ptr(k), _lib.ptr(v), _lib.ptr(out), _lib.ptr(lse),
+              _lib.ptr(acc_o), _lib.ptr(acc_m), _lib.ptr(acc_l), B, H, Sq, Sk, D, int(q_pos0), int(k_pos0),
+              int(bool(causal)), _lib.ptr(bias), 0 if bias is None else bias.shape[1], _lib.ptr(seg),
+              0 if seg is None else seg.shape[1], 1.0 / math.sqrt(D), int(first), int(last),
+              _lib.stream_ptr(stream))
+
+
+def bwd_prep(out, dout, delta, stream=None):
+    B, Sq, H, D = out.shape
+    _lib.call("lwm_attn_bwd_prep", _lib.ptr(out), _lib.ptr(dout), _lib.ptr(delta), B, H, Sq, D,
+              _lib.stream_ptr(stream))
+
+
+def bwd_step(q, k, v, dout, lse, delta, dq_acc, dk_acc, dv_acc, q_pos0, k_pos0, causal, bias, seg, stream=None):
+    B, Sq, H, D = q.shape
+    Sk = k.shape[1]
+    _lib.call("lwm_attn_bwd_step", _lib.ptr(q), _lib.ptr(k), _lib.ptr(v), _lib.ptr(dout), _lib.ptr(lse),
+              _lib.ptr(delta), _lib.ptr(dq_acc), _lib.ptr(dk_acc), _lib.ptr(dv_acc), B, H, Sq, Sk, D,
+              int(q_pos0), int(k_pos0), int(bool(causal)), _lib.ptr(bias),
+              0 if bias is None else bias.shape[1], _lib.ptr(seg), 0 if seg is None else seg.shape[1],
+              1.0 / math.sqrt(D), _lib.stream_ptr(stream))
+
+
+def cast_f32_to_bf16(src, dst, stream=None):
+    _lib.call("lwm_cast_f32_to_bf16", _lib.ptr(src), _lib.ptr(dst), src.numel(), _lib.stream_ptr(stream))
+
+
+# ------------------------------------------------------------------------------------------------
+# ring drivers
+# ------------------------------------------------------------------------------------------------
+def _ring_exchange(send_tensors, recv_tensors, group, rank, world):
+    """One hop i -> i+1 of every tensor in the list (lax.ppermute of the reference)."""
+    nxt = dist.get_global_rank(group, (rank + 1) % world) if group is not dist.group.WORLD else (rank + 1) % world
+    prv = dist.get_global_rank(group, (rank - 1) % world) if group is not dist.group.WORLD else (rank - 1) % world
+    ops = []
+    for s, r in zip(send_tensors, recv_tensors):
+        ops.append(dist.P2POp(dist.isend, s, nxt, group))
+        ops.append(dist.P2POp(dist.irecv, r, prv, group))
+    return dist.batch_isend_irecv(ops)
+
+
+def ring_forward(q, k, v, bias, seg, causal, group, rank, world, layout="auto"):
+    B, Sq, H, D = q.shape
+    Sk = k.shape[1]
+    out = torch.empty_like(q)
+    lse = torch.empty((B, H, Sq), dtype=torch.float32, device=q.device)
+    if world == 1:
+        fwd_step(q, k, v, out, lse, None, None, None, 0, 0, causal, bias, seg, True, True)
+        return out, lse
+    plan = rs.make_plan(world, rank, Sq, Sk, causal, layout)
+    return rs.run_forward(plan, q, k, v, out, lse, bias, seg, causal, group, rank, world, fwd_step, _ring_exchange)
+
+
+def ring_backward(q, k, v, out, lse, dout, bias, seg, causal, group, rank, world, layout="auto"):
+    B, Sq, H, D = q.shape
+    Sk = k.shape[1]
+    dev = q.device
+    delta = torch.empty((B, H, Sq), dtype=torch.float32, device=dev)
+    bwd_prep(out, dout, delta)
+    if world == 1:
+        dq_acc = torch.zeros((B, Sq, H, D), dtype=torch.float32, device=dev)
+        dk_acc = torch.zeros((B, Sk, H, D), dtype=torch.float32, device=dev)
+        dv_acc = torch.zeros((B, Sk, H, D), dtype=torch.float32, device=dev)
+        bwd_step(q, k, v, dout, lse, delta, dq_acc, dk_acc, dv_acc, 0, 0, causal, bias, seg)
+        dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+        cast_f32_to_bf16(dq_acc, dq)
+        cast_f32_to_bf16(dk_acc, dk)
+        cast_f32_to_bf16(dv_acc, dv)
+        return dq, dk, dv
+    plan = rs.make_plan(world, rank, Sq, Sk, causal, layout)
+    return rs.run_backward(plan, q, k, v, dout, lse, delta, bias, seg, causal, group, rank, world, bwd_step,
+                           cast_f32_to_bf16, _ring_exchange)

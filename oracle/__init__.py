@@ -1,0 +1,14 @@
+"""CPU oracle — TEST INFRASTRUCTURE ONLY.
+
+Restatements of the reference algorithms used solely as checkers by tests/, by
+__graft_entry__.smoke() and by bench.py's cpu_baseline / --impl reference legs. Nothing under
+lwm_b200/ may import this package: the product path is the CUDA library or a loud failure.
+
+PARITY UNPINNED: the reference ships no tests / golden vectors, the ring-attention arithmetic
+lives in the un-vendored, un-pinned `ringattention` pip package (gpu_requirements.txt:8), and
+jax/flax cannot be imported in the build container (no network, wheelhouse excludes jax), so the
+oracle could not be checked against outputs of the reference itself. It is pinned instead against
+(a) an independent dense fp64 formulation, (b) torch's own CPU operators
+(scaled_dot_product_attention / conv2d / group_norm) and (c) mathematical invariants — see
+tests/test_oracle_*.py and DESIGN.md.
+"""
