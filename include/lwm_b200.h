@@ -83,6 +83,8 @@ int lwm_attn_bwd_step(const void* q, const void* k, const void* v, const void* d
 
 /* Element-wise helpers used by the ring host loop. */
 int lwm_cast_f32_to_bf16(const float* src, void* dst, long long n, void* stream);
+/* dst[i] += src[i] (fp32, n % 4 == 0): folds a dK/dV partial received from a peer into the owner's accumulator. */
+int lwm_add_f32(float* dst, const float* src, long long n, void* stream);
 
 #ifdef __cplusplus
 }

@@ -20,6 +20,7 @@ _SIGNATURES = {
     "lwm_attn_bwd_step": [c_void_p] * 9 + [c_int] * 5 + [c_ll, c_ll, c_int, c_void_p, c_ll, c_void_p, c_ll,
                                                        c_float, c_void_p],
     "lwm_cast_f32_to_bf16": [c_void_p, c_void_p, c_ll, c_void_p],
+    "lwm_add_f32": [c_void_p, c_void_p, c_ll, c_void_p],
 }
 
 

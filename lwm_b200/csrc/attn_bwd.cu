@@ -1,0 +1,411 @@
+// Ring-attention backward tile kernel for sm_100a.
+//
+// One launch = one ring step of the reference's custom_vjp backward (SURVEY.md Appendix A `bwd`;
+// the op is bound at lwm/llama.py:541): for the held K/V block, recompute P from (q, k, lse) and
+// accumulate dV += P^T dO, dK += dS^T Q / sqrt(D), dQ += dS K / sqrt(D) with
+// dS = P o (dO V^T - rowsum(dO o O)).
+//
+// Mapping to the hardware (K/V-stationary, everything computed TRANSPOSED so that the key index
+// sits on the TMEM lanes and P^T can feed the dV MMA straight from TMEM):
+//   CTA = one 128-key tile of one (batch, head); loop over the 128-row Q tiles that can see it.
+//   Five UMMAs (128x128x128, bf16 in, fp32 acc) per Q tile:
+//     S^T  = K  Q^T     SS  K-major x K-major                          -> TMEM R0
+//     dP^T = V  dO^T    SS  K-major x K-major                          -> TMEM R1
+//     dV  += P^T dO     TS  (P^T bf16 written over S^T in R0) x dO MN-major
+//     dK  += dS^T Q     SS  dS^T from smem (K-major)  x Q MN-major
+//     dQ   = dS  K      SS  the SAME smem tile read MN-major x K MN-major -> TMEM R1 (dP^T is dead)
+//   TMEM: R0 | R1 | dK | dV = 512 columns.
+//   warps 0-3 / 4-7: key row = TMEM lane; the two warpgroups split the 128 query columns. They
+//     compute P^T, dS^T and drain dQ: TMEM -> swizzled smem -> TMA reduce-add (fp32) into dq_acc.
+//   warp 8: TMA loads (K,V once; Q + lse + delta double-buffered; dO single-buffered);
+//   warp 9: one lane issues the UMMAs.
+// The softmax scale is folded into dS before it is rounded to bf16, so dK and dQ need no epilogue
+// scaling. dk_acc / dv_acc are accumulated read-modify-write by the one CTA that owns the tile.
+#include "attn_common.cuh"
+#include "tmap.h"
+#include "capi_internal.h"
+
+namespace lwm {
+
+struct BwdParams {
+  int B, H, Sq, Sk;
+  float scale;       // softmax_scale
+  float scale_log2;  // softmax_scale * log2(e)
+  MaskParams mask;
+  const float* lse;    // [B,H,Sq] natural log
+  const float* delta;  // [B,H,Sq]
+  float* dk_acc;       // [B,Sk,H,D] fp32
+  float* dv_acc;       // [B,Sk,H,D] fp32
+};
+
+constexpr int kBwdThreads = 384;
+constexpr int kTB = kTile * kHeadDim * 2;  // 32 KB bf16 tile
+// smem map (bytes): K | V | Q0 | Q1 | dO | dS (2 x 16K halves) | stage (2 x 16K)
+constexpr int kOffK = 0, kOffV = kTB, kOffQ = 2 * kTB, kOffDO = 4 * kTB, kOffDS = 5 * kTB, kOffStage = 6 * kTB;
+constexpr int kOffLse = 7 * kTB, kOffDelta = kOffLse + 2 * kTile * 4, kOffBars = kOffDelta + 2 * kTile * 4;
+constexpr int kBwdSmemBytes = kOffBars + 256;  // 231,680 B of the 232,448 B a CTA may own
+
+struct BwdBarriers {
+  uint64_t kv_full;
+  uint64_t q_full[2], q_empty[2];
+  uint64_t do_full, do_empty;
+  uint64_t s_full, dp_full;
+  uint64_t p_ready, ds_ready;
+  uint64_t dq_full, dq_drained;
+  uint64_t final_bar;
+};
+
+LWM_DEVICE void load_tile_nb(uint8_t* dst, const CUtensorMap* tm, uint64_t* bar, int h, int row0, int b) {
+  tma_load_4d(dst, tm, bar, 0, h, row0, b);
+  tma_load_4d(dst + kTB / 2, tm, bar, 64, h, row0, b);
+}
+
+__global__ void __launch_bounds__(kBwdThreads, 1)
+attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO,
+                const __grid_constant__ CUtensorMap tmDQ, const BwdParams p) {
+  // no static shared memory in this kernel: the dynamic window starts 1024-aligned (checked below)
+  extern __shared__ __align__(1024) uint8_t smem[];
+  float (*s_lse)[kTile] = reinterpret_cast<float (*)[kTile]>(smem + kOffLse);
+  float (*s_delta)[kTile] = reinterpret_cast<float (*)[kTile]>(smem + kOffDelta);
+  BwdBarriers& bars = *reinterpret_cast<BwdBarriers*>(smem + kOffBars);
+  uint32_t& tmem_base_s = *reinterpret_cast<uint32_t*>(smem + kOffBars + 192);
+  if (smem_u32(smem) & 1023u) __trap();
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int n = blockIdx.x;  // kv tile (ascending = heaviest first under causal masking)
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int n_q_tiles = p.Sq / kTile;
+  // first Q tile with a row that can see key 0 of this tile
+  int i_start = 0;
+  if (p.mask.causal) {
+    const long long diff = (long long)p.mask.k_pos0 + (long long)n * kTile - p.mask.q_pos0;
+    i_start = diff <= 0 ? 0 : int(min(diff / kTile, (long long)n_q_tiles));
+  }
+  const int nq = n_q_tiles - i_start;
+  if (nq <= 0) return;  // this key tile is invisible to the whole q shard: dk/dv unchanged
+
+  if (warp == 9) {
+    tmem_alloc<512>(&tmem_base_s);
+  } else if (warp == 8 && lane == 0) {
+    mbar_init(&bars.kv_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&bars.q_full[s], 1);
+      mbar_init(&bars.q_empty[s], 1);
+    }
+    mbar_init(&bars.do_full, 1);
+    mbar_init(&bars.do_empty, 1);
+    mbar_init(&bars.s_full, 1);
+    mbar_init(&bars.dp_full, 1);
+    mbar_init(&bars.p_ready, 256);
+    mbar_init(&bars.ds_ready, 256);
+    mbar_init(&bars.dq_full, 1);
+    mbar_init(&bars.dq_drained, 256);
+    mbar_init(&bars.final_bar, 1);
+    fence_mbar_init();
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    tma_prefetch_desc(&tmDO);
+    tma_prefetch_desc(&tmDQ);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+  constexpr uint32_t R0 = 0, R1 = 128, RDK = 256, RDV = 384;
+
+  if (warp >= 8) {
+    setmaxnreg_dec<56>();
+    if (warp == 8) {
+      // ---------------------------------------------------------------- TMA producer
+      if (lane == 0) {
+        mbar_arrive_expect_tx(&bars.kv_full, 2 * kTB);
+        load_tile_nb(smem + kOffK, &tmK, &bars.kv_full, h, n * kTile, b);
+        load_tile_nb(smem + kOffV, &tmV, &bars.kv_full, h, n * kTile, b);
+        const long long ml_base = ((long long)b * p.H + h) * p.Sq;
+        for (int it = 0; it < nq; ++it) {
+          const int st = it & 1;
+          const int row0 = (i_start + it) * kTile;
+          mbar_wait(&bars.q_empty[st], ((it >> 1) & 1) ^ 1);
+          mbar_arrive_expect_tx(&bars.q_full[st], kTB + 2 * kTile * 4);
+          load_tile_nb(smem + kOffQ + st * kTB, &tmQ, &bars.q_full[st], h, row0, b);
+          bulk_load_1d(s_lse[st], p.lse + ml_base + row0, kTile * 4, &bars.q_full[st]);
+          bulk_load_1d(s_delta[st], p.delta + ml_base + row0, kTile * 4, &bars.q_full[st]);
+          mbar_wait(&bars.do_empty, (it & 1) ^ 1);
+          mbar_arrive_expect_tx(&bars.do_full, kTB);
+          load_tile_nb(smem + kOffDO, &tmDO, &bars.do_full, h, row0, b);
+        }
+      }
+    } else if (warp == 9) {
+      // ---------------------------------------------------------------- UMMA issuer
+      if (lane == 0) {
+        constexpr uint32_t id_kk = make_idesc_bf16(kTile, kTile, false, false);     // S^T, dP^T
+        constexpr uint32_t id_kn = make_idesc_bf16(kTile, kHeadDim, false, true);   // dV (A tmem), dK
+        constexpr uint32_t id_nn = make_idesc_bf16(kTile, kHeadDim, true, true);    // dQ
+        const uint32_t aK = smem_u32(smem + kOffK), aV = smem_u32(smem + kOffV), aDO = smem_u32(smem + kOffDO),
+                       aDS = smem_u32(smem + kOffDS);
+        auto koff = [](int ks) { return uint32_t((ks >> 2) * (kTB / 2) + (ks & 3) * 32); };
+        auto issue_st = [&](int it) {
+          const uint32_t aQ = smem_u32(smem + kOffQ + (it & 1) * kTB);
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks)
+            umma_ss(tmem + R0, desc_kmajor_sw128(aK + koff(ks)), desc_kmajor_sw128(aQ + koff(ks)), id_kk, ks > 0);
+          umma_commit(&bars.s_full);
+        };
+        mbar_wait(&bars.kv_full, 0);
+        mbar_wait(&bars.q_full[0], 0);
+        tc_fence_after();
+        issue_st(0);
+        for (int it = 0; it < nq; ++it) {
+          const uint32_t aQ = smem_u32(smem + kOffQ + (it & 1) * kTB);
+          mbar_wait(&bars.do_full, it & 1);
+          if (it > 0) mbar_wait(&bars.dq_drained, (it - 1) & 1);
+          tc_fence_after();
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks)  // dP^T = V dO^T
+            umma_ss(tmem + R1, desc_kmajor_sw128(aV + koff(ks)), desc_kmajor_sw128(aDO + koff(ks)), id_kk, ks > 0);
+          umma_commit(&bars.dp_full);
+          mbar_wait(&bars.p_ready, it & 1);
+          tc_fence_after();
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks)  // dV += P^T dO ; P^T halves live at R0+[0,32) and R0+[64,96)
+            umma_ts(tmem + RDV, tmem + R0 + (ks >> 2) * 64 + (ks & 3) * 8,
+                    desc_mnmajor_sw128(aDO + ks * 2048, kTB / 2), id_kn, (it > 0) || ks > 0);
+          umma_commit(&bars.do_empty);
+          if (it + 1 < nq) {
+            mbar_wait(&bars.q_full[(it + 1) & 1], ((it + 1) >> 1) & 1);
+            tc_fence_after();
+            issue_st(it + 1);
+          }
+          mbar_wait(&bars.ds_ready, it & 1);
+          tc_fence_after();
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks)  // dK += dS^T Q
+            umma_ss(tmem + RDK, desc_kmajor_sw128(aDS + koff(ks)), desc_mnmajor_sw128(aQ + ks * 2048, kTB / 2),
+                    id_kn, (it > 0) || ks > 0);
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks)  // dQ = dS K
+            umma_ss(tmem + R1, desc_mnmajor_sw128(aDS + ks * 2048, kTB / 2),
+                    desc_mnmajor_sw128(aK + ks * 2048, kTB / 2), id_nn, ks > 0);
+          umma_commit(&bars.dq_full);
+          umma_commit(&bars.q_empty[it & 1]);
+        }
+        umma_commit(&bars.final_bar);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ compute warpgroups
+    setmaxnreg_inc<224>();
+    const int wg = warp >> 2;                  // 0: query columns [0,64) ; 1: [64,128)
+    const int r = threadIdx.x & (kTile - 1);   // TMEM lane = key row (S^T, dP^T, dK, dV) / query row (dQ)
+    const uint32_t lane_off = uint32_t((warp & 3) * 32) << 16;
+    const uint32_t tR0 = tmem + lane_off + R0 + wg * 64;
+    const uint32_t tR1 = tmem + lane_off + R1 + wg * 64;
+    const long long k_pos = (long long)p.mask.k_pos0 + (long long)n * kTile + r;  // this thread's key
+    const bool has_bias = p.mask.bias != nullptr, has_seg = p.mask.seg != nullptr;
+    const int* seg_row = has_seg ? p.mask.seg + (long long)b * p.mask.seg_stride : nullptr;
+    const int my_seg = has_seg ? seg_row[k_pos] : 0;
+    float bias_t = 0.f;
+    bool key_masked = false;
+    if (has_bias) {
+      bias_t = p.mask.bias[(long long)b * p.mask.bias_stride + k_pos] * kLog2e;
+      key_masked = bias_t < kMaskedLogit;
+    }
+    uint8_t* my_ds = smem + kOffDS + wg * (kTB / 2);        // this warpgroup's half of the dS^T tile
+    uint8_t* my_stage = smem + kOffStage + wg * (kTB / 2);  // + its dedicated staging chunk
+    const bool is_issuer = (threadIdx.x & 127) == 0;
+
+    for (int it = 0; it < nq; ++it) {
+      const int st = it & 1;
+      const int q_tile_row0 = (i_start + it) * kTile;
+      const long long q_tile_pos = (long long)p.mask.q_pos0 + q_tile_row0;
+      const bool need_mask = has_bias || has_seg ||
+                             (p.mask.causal && (q_tile_pos < (long long)p.mask.k_pos0 + (long long)n * kTile + kTile - 1));
+      // ---- A) P^T = exp2(S^T * scale_log2 (+bias) - lse2)
+      mbar_wait(&bars.q_full[st], (it >> 1) & 1);  // lse / delta of this Q tile are in smem
+      mbar_wait(&bars.s_full, it & 1);
+      tc_fence_after();
+      float pr[64];
+      {
+        uint32_t s[2][32];
+        tmem_ld_x32(tR0, s[0]);
+        tmem_ld_x32(tR0 + 32, s[1]);
+        tmem_wait_ld();
+        const float4* lse4 = reinterpret_cast<const float4*>(&s_lse[st][wg * 64]);
+#pragma unroll
+        for (int c4 = 0; c4 < 16; ++c4) {
+          const float4 l4 = lse4[c4];
+          const float ls[4] = {l4.x, l4.y, l4.z, l4.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int c = c4 * 4 + e;
+            // lse at the masked level (row never saw an unmasked key; padded rows in the reference):
+            // fp32 cannot resolve logits against it, so such rows get p = 0, i.e. no gradient
+            const float nl2 = (ls[e] < -1.0e29f) ? -INFINITY : -ls[e] * kLog2e;
+            float tv = __uint_as_float(s[c >> 5][c & 31]) * p.scale_log2;
+            if (need_mask) {
+              tv = key_masked ? kMaskedLogit : tv + bias_t;
+              const long long q_pos = q_tile_pos + wg * 64 + c;
+              if (has_seg && seg_row[q_pos] != my_seg) tv = kMaskedLogit;
+              if (p.mask.causal && q_pos < k_pos) tv = kMaskedLogit;
+            }
+            pr[c] = ex2f(tv + nl2);
+          }
+        }
+        uint32_t pk[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) pk[i] = pack_bf16x2(pr[2 * i], pr[2 * i + 1]);
+        tmem_st_x32(tR0, pk);  // P^T half: 32 packed columns at the start of this warpgroup's S^T half
+        tmem_wait_st();
+        tc_fence_before();
+        mbar_arrive(&bars.p_ready);
+      }
+      // ---- B) dS^T = P^T o (dP^T - delta) * scale  -> smem (bf16, 128B-swizzled K-major tile)
+      mbar_wait(&bars.dp_full, it & 1);
+      tc_fence_after();
+      {
+        uint32_t d[2][32];
+        tmem_ld_x32(tR1, d[0]);
+        tmem_ld_x32(tR1 + 32, d[1]);
+        tmem_wait_ld();
+        if (it > 0) {
+          // the previous drain's TMA reduce must have finished reading this warpgroup's buffers
+          if (is_issuer) tma_wait_group_read<0>();
+          named_bar_sync(1 + wg, 128);
+        }
+        const float4* dl4 = reinterpret_cast<const float4*>(&s_delta[st][wg * 64]);
+#pragma unroll
+        for (int c16 = 0; c16 < 8; ++c16) {  // 8 bf16 (16 B) per store
+          float dsv[8];
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            const float4 d4 = dl4[c16 * 2 + hh];
+            const float dl[4] = {d4.x, d4.y, d4.z, d4.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int c = c16 * 8 + hh * 4 + e;
+              dsv[hh * 4 + e] = pr[c] * (__uint_as_float(d[c >> 5][c & 31]) - dl[e]) * p.scale;
+            }
+          }
+          const uint4 v4 = make_uint4(pack_bf16x2(dsv[0], dsv[1]), pack_bf16x2(dsv[2], dsv[3]),
+                                      pack_bf16x2(dsv[4], dsv[5]), pack_bf16x2(dsv[6], dsv[7]));
+          *reinterpret_cast<uint4*>(my_ds + swz128_offset(r, c16)) = v4;
+        }
+        fence_proxy_async_smem();
+        mbar_arrive(&bars.ds_ready);
+      }
+      // ---- C) drain dQ (rows = queries) : TMEM -> smem (fp32, 32-column swizzled chunks) -> TMA reduce-add
+      mbar_wait(&bars.dq_full, it & 1);
+      tc_fence_after();
+      {
+        uint32_t a[2][32];
+        tmem_ld_x32(tR1, a[0]);
+        tmem_ld_x32(tR1 + 32, a[1]);
+        tmem_wait_ld();
+        tc_fence_before();
+        mbar_arrive(&bars.dq_drained);  // R1 may be overwritten by the next dP^T
+#pragma unroll
+        for (int ch = 0; ch < 2; ++ch) {
+          uint8_t* dst = ch == 0 ? my_stage : my_ds;  // dS^T half is dead once dq_full fired
+#pragma unroll
+          for (int c16 = 0; c16 < 8; ++c16)
+            *reinterpret_cast<uint4*>(dst + swz128_offset(r, c16)) =
+                make_uint4(a[ch][4 * c16], a[ch][4 * c16 + 1], a[ch][4 * c16 + 2], a[ch][4 * c16 + 3]);
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(1 + wg, 128);
+        if (is_issuer) {
+          tma_reduce_add_4d(&tmDQ, my_stage, wg * 64, h, q_tile_row0, b);
+          tma_reduce_add_4d(&tmDQ, my_ds, wg * 64 + 32, h, q_tile_row0, b);
+          tma_commit_group();
+        }
+      }
+    }
+    // ------------------------------------------------------------------ epilogue: dK (wg 0) / dV (wg 1)
+    mbar_wait(&bars.final_bar, 0);
+    tc_fence_after();
+    {
+      const uint32_t tAcc = tmem + lane_off + (wg == 0 ? RDK : RDV);
+      float* acc = (wg == 0 ? p.dk_acc : p.dv_acc) +
+                   ((((long long)b * p.Sk + (long long)n * kTile + r) * p.H + h) * kHeadDim);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t o[32];
+        tmem_ld_x32(tAcc + c * 32, o);
+        tmem_wait_ld();
+        float4* dst = reinterpret_cast<float4*>(acc + c * 32);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float4 cur = dst[i];
+          cur.x += __uint_as_float(o[4 * i]);
+          cur.y += __uint_as_float(o[4 * i + 1]);
+          cur.z += __uint_as_float(o[4 * i + 2]);
+          cur.w += __uint_as_float(o[4 * i + 3]);
+          dst[i] = cur;
+        }
+      }
+    }
+    if (is_issuer) tma_wait_group<0>();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) tmem_dealloc<512>(tmem);
+}
+
+static bool make_bf16_tmap(CUtensorMap* tm, const void* ptr, int B, int S, int H) {
+  uint64_t dims[4] = {uint64_t(kHeadDim), uint64_t(H), uint64_t(S), uint64_t(B)};
+  uint64_t strides[3] = {uint64_t(kHeadDim) * 2, uint64_t(H) * kHeadDim * 2, uint64_t(S) * H * kHeadDim * 2};
+  uint32_t box[4] = {64, 1, uint32_t(kTile), 1};
+  return encode_tmap(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, ptr, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+}
+static bool make_f32_tmap(CUtensorMap* tm, const void* ptr, int B, int S, int H) {
+  // fp32 [B,S,H,128]: one box = 32 columns (128 B) x 128 rows of one head, 128B swizzle
+  uint64_t dims[4] = {uint64_t(kHeadDim), uint64_t(H), uint64_t(S), uint64_t(B)};
+  uint64_t strides[3] = {uint64_t(kHeadDim) * 4, uint64_t(H) * kHeadDim * 4, uint64_t(S) * H * kHeadDim * 4};
+  uint32_t box[4] = {32, 1, uint32_t(kTile), 1};
+  return encode_tmap(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, ptr, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+}
+
+}  // namespace lwm
+
+using namespace lwm;
+
+extern "C" int lwm_attn_bwd_step(const void* q, const void* k, const void* v, const void* dout, const float* lse,
+                                 const float* delta, float* dq_acc, float* dk_acc, float* dv_acc, int B, int H,
+                                 int Sq, int Sk, int D, long long q_pos0, long long k_pos0, int causal,
+                                 const float* bias, long long bias_stride, const int* segment_ids,
+                                 long long seg_stride, float softmax_scale, void* stream) {
+  if (!lwm_check_device()) return LWM_ERR_DEVICE;
+  if (D != kHeadDim) return lwm_fail(LWM_ERR_SHAPE, "attn_bwd: head_dim must be 128");
+  if (B <= 0 || H <= 0 || Sq <= 0 || Sk <= 0 || Sq % kTile || Sk % kTile)
+    return lwm_fail(LWM_ERR_SHAPE, "attn_bwd: Sq and Sk must be positive multiples of 128");
+  if (!q || !k || !v || !dout || !lse || !delta || !dq_acc || !dk_acc || !dv_acc)
+    return lwm_fail(LWM_ERR_ARG, "attn_bwd: null pointer");
+  if (q_pos0 + Sq > 0x7fffffffLL || k_pos0 + Sk > 0x7fffffffLL)
+    return lwm_fail(LWM_ERR_SHAPE, "attn_bwd: global positions must fit in int32");
+  CUtensorMap tq, tk, tv, tdo, tdq;
+  if (!make_bf16_tmap(&tq, q, B, Sq, H) || !make_bf16_tmap(&tk, k, B, Sk, H) || !make_bf16_tmap(&tv, v, B, Sk, H) ||
+      !make_bf16_tmap(&tdo, dout, B, Sq, H) || !make_f32_tmap(&tdq, dq_acc, B, Sq, H))
+    return lwm_fail(LWM_ERR_CUDA, "attn_bwd: cuTensorMapEncodeTiled failed (pointers must be 16B aligned)");
+  BwdParams p;
+  p.B = B; p.H = H; p.Sq = Sq; p.Sk = Sk;
+  p.scale = softmax_scale;
+  p.scale_log2 = softmax_scale * kLog2e;
+  p.mask.q_pos0 = int(q_pos0); p.mask.k_pos0 = int(k_pos0); p.mask.causal = causal;
+  p.mask.bias = bias; p.mask.bias_stride = bias_stride;
+  p.mask.seg = segment_ids; p.mask.seg_stride = seg_stride;
+  p.lse = lse; p.delta = delta; p.dk_acc = dk_acc; p.dv_acc = dv_acc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmemBytes) !=
+        cudaSuccess)
+      return lwm_fail(LWM_ERR_CUDA, "attn_bwd: cannot raise dynamic shared memory limit");
+    attr_set = true;
+  }
+  dim3 grid(Sk / kTile, H, B);
+  attn_bwd_kernel<<<grid, kBwdThreads, kBwdSmemBytes, reinterpret_cast<cudaStream_t>(stream)>>>(tq, tk, tv, tdo,
+                                                                                                tdq, p);
+  return lwm_check_launch("attn_bwd_kernel");
+}

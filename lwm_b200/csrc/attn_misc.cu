@@ -41,6 +41,16 @@ __global__ void cast_f32_bf16_kernel(const float4* __restrict__ src, uint2* __re
   }
 }
 
+__global__ void add_f32_kernel(float4* __restrict__ dst, const float4* __restrict__ src, long long n4) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
+       i += (long long)gridDim.x * blockDim.x) {
+    float4 a = dst[i];
+    const float4 b = src[i];
+    a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    dst[i] = a;
+  }
+}
+
 }  // namespace lwm
 
 using namespace lwm;
@@ -68,4 +78,17 @@ extern "C" int lwm_cast_f32_to_bf16(const float* src, void* dst, long long n, vo
   cast_f32_bf16_kernel<<<blocks, threads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const float4*>(src), reinterpret_cast<uint2*>(dst), n4);
   return lwm_check_launch("cast_f32_bf16_kernel");
+}
+
+extern "C" int lwm_add_f32(float* dst, const float* src, long long n, void* stream) {
+  if (!lwm_check_device()) return LWM_ERR_DEVICE;
+  if (n % 4) return lwm_fail(LWM_ERR_SHAPE, "add_f32: n must be a multiple of 4");
+  if (n == 0) return LWM_OK;
+  const long long n4 = n / 4;
+  const int threads = 256;
+  const long long want = (n4 + threads - 1) / threads;
+  const unsigned blocks = unsigned(want < 148LL * 16 ? want : 148LL * 16);
+  add_f32_kernel<<<blocks, threads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<float4*>(dst), reinterpret_cast<const float4*>(src), n4);
+  return lwm_check_launch("add_f32_kernel");
 }

@@ -1,13 +1,141 @@
-"""Ring schedules (placeholder — filled in with the multi-GPU path)."""
+"""Ring schedules for the sequence-parallel attention op (host logic only — no numerics here).
+
+The reference rotates K/V one hop per step with lax.ppermute, because a
+TPU torus only has neighbour links. On an NVSwitch box every peer is one hop away at full
+bandwidth, so the "ring" is only a SCHEDULE: at step `idx` rank r needs the K/V block that
+originated on rank (r - idx) mod P. We fetch it straight from its owner (one NCCL send/recv
+pair per block, posted one step ahead on a side stream, double-buffered against the tile
+kernels) instead of forwarding it hop by hop; K/V are never modified, so there is no chained
+dependency between steps. In the backward the dK/dV partial of a block is pushed straight back
+to the block's owner, which accumulates it (the reference lets dk/dv ride the ring instead).
+
+Two schedules, identical inputs/outputs (contiguous sequence shards, lwm/llama.py:559-566):
+  contiguous  the reference's work assignment: rank r computes its own rows against blocks
+              0..r. Causal work is unbalanced (rank P-1 does 2P-1 times the work of rank 0).
+  zigzag      the sequence is cut in 2P half-chunks; rank r COMPUTES query chunks r and
+              2P-1-r, which makes every rank's causal work identical at every step. Only Q
+              (and dO) are permuted on entry and O (and dQ) on exit; K/V half-chunks are pulled
+              from their contiguous owners directly and dK/dV partials pushed back to them.
+
+The plan is a pure function of (world, rank, sizes, causal, layout): every rank derives the
+same global picture, so sends and receives always match without negotiation.
+"""
+from dataclasses import dataclass, field
+from typing import List, Tuple
 
 
-def make_plan(world, rank, Sq, Sk, causal, layout):
-    raise NotImplementedError
+def visible(q_pos0, q_len, k_pos0, causal):
+    """Does any query of the chunk see any key of the chunk (token-level causal mask)?"""
+    return (not causal) or (q_pos0 + q_len - 1 >= k_pos0)
 
 
-def run_forward(*a, **k):
-    raise NotImplementedError
+@dataclass
+class KvRef:
+    owner: int      # rank holding the block in the contiguous layout
+    start: int      # local row offset inside the owner's shard
+    length: int
+    pos0: int       # global token position of its first row
 
 
-def run_backward(*a, **k):
-    raise NotImplementedError
+@dataclass
+class QRef:
+    owner: int      # rank whose contiguous shard holds these rows
+    start: int
+    length: int
+    pos0: int
+
+
+@dataclass
+class Step:
+    kv: List[KvRef] = field(default_factory=list)              # blocks this rank consumes
+    sends: List[Tuple[int, int, int]] = field(default_factory=list)  # (start, length, peer) of my shard
+    pairs: List[Tuple[int, int]] = field(default_factory=list)  # (q chunk idx, kv idx in `kv`)
+
+
+@dataclass
+class Plan:
+    world: int
+    rank: int
+    layout: str
+    q_chunks: List[QRef]             # query chunks this rank computes
+    q_sends: List[Tuple[int, int, int]]  # (start, length, peer): rows of MY shard computed elsewhere
+    steps: List[Step]
+
+
+def choose_layout(world, Sq, Sk, causal, layout):
+    if layout == "auto":
+        layout = "zigzag" if (causal and world > 1 and Sq == Sk and Sq % 256 == 0) else "contiguous"
+    if layout == "zigzag" and not (Sq == Sk and Sq % 256 == 0):
+        raise ValueError("zigzag layout needs Sq == Sk and a shard length divisible by 256")
+    if layout not in ("contiguous", "zigzag"):
+        raise ValueError("unknown layout %r" % (layout,))
+    return layout
+
+
+def _zig(c, P):
+    """rank that COMPUTES half-chunk c (0 <= c < 2P) in the zigzag assignment."""
+    return c if c < P else 2 * P - 1 - c
+
+
+def compute_chunks(world, rank, Sq, layout):
+    """Query chunks computed by `rank` (as references into the contiguous shards)."""
+    if layout == "contiguous":
+        return [QRef(rank, 0, Sq, rank * Sq)]
+    h = Sq // 2
+    return [QRef(c // 2, (c % 2) * h, h, c * h) for c in (rank, 2 * world - 1 - rank)]
+
+
+def step_kv(world, rank, idx, Sk, layout):
+    """K/V blocks rank `rank` consumes at step idx (before visibility filtering)."""
+    src = (rank - idx) % world
+    if layout == "contiguous":
+        return [KvRef(src, 0, Sk, src * Sk)]
+    h = Sk // 2
+    return [KvRef(c // 2, (c % 2) * h, h, c * h) for c in (src, 2 * world - 1 - src)]
+
+
+def make_plan(world, rank, Sq, Sk, causal, layout="auto"):
+    layout = choose_layout(world, Sq, Sk, causal, layout)
+    q_chunks = compute_chunks(world, rank, Sq, layout)
+    # rows of my contiguous shard that another rank computes
+    q_sends = []
+    for peer in range(world):
+        if peer == rank:
+            continue
+        for qc in compute_chunks(world, peer, Sq, layout):
+            if qc.owner == rank:
+                q_sends.append((qc.start, qc.length, peer))
+    steps = []
+    for idx in range(world):
+        st = Step()
+        for kv in step_kv(world, rank, idx, Sk, layout):
+            needed = [qi for qi, qc in enumerate(q_chunks) if visible(qc.pos0, qc.length, kv.pos0, causal)]
+            if needed:
+                st.kv.append(kv)
+                st.pairs.extend((qi, len(st.kv) - 1) for qi in needed)
+        # what do the OTHER ranks need from my shard at this step?
+        for peer in range(world):
+            if peer == rank:
+                continue
+            peer_q = compute_chunks(world, peer, Sq, layout)
+            for kv in step_kv(world, peer, idx, Sk, layout):
+                if kv.owner == rank and any(visible(qc.pos0, qc.length, kv.pos0, causal) for qc in peer_q):
+                    st.sends.append((kv.start, kv.length, peer))
+        steps.append(st)
+    return Plan(world, rank, layout, q_chunks, q_sends, steps)
+
+
+def work_units(plan, causal):
+    """Causal work (in units of full chunk x chunk tiles; a diagonal pair counts 1/2) per step —
+    used by the tests to assert the balance property of the zigzag schedule."""
+    out = []
+    for st in plan.steps:
+        w = 0.0
+        for qi, ki in st.pairs:
+            qc, kv = plan.q_chunks[qi], st.kv[ki]
+            if causal and kv.pos0 + kv.length - 1 > qc.pos0:   # straddles the diagonal
+                w += 0.5 * qc.length * kv.length
+            else:
+                w += 1.0 * qc.length * kv.length
+        out.append(w)
+    return out

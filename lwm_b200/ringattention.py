@@ -22,6 +22,7 @@ import torch
 import torch.distributed as dist
 
 from . import _lib
+from . import ring_exec as rx
 from . import ring_schedule as rs
 
 _AXIS_GROUPS = {}
@@ -71,17 +72,24 @@ class _RingAttnFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, q, k, v, bias, seg, causal, axis_name, layout):
         group, rank, world = _resolve_group(axis_name)
-        out, lse = ring_forward(q, k, v, bias, seg, causal, group, rank, world, layout)
-        ctx.save_for_backward(q, k, v, out, lse, bias, seg)
+        out, res = ring_forward(q, k, v, bias, seg, causal, group, rank, world, layout)
+        # residuals stay in the schedule's compute layout (zigzag chunks), so the backward only has
+        # to permute dout on entry and dq on exit
+        ctx.n_chunks = len(res["q_chunks"])
+        ctx.save_for_backward(k, v, bias, seg, *res["q_chunks"], *res["out_chunks"], *res["lse_chunks"])
         ctx.causal, ctx.axis_name, ctx.layout = causal, axis_name, layout
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        q, k, v, out, lse, bias, seg = ctx.saved_tensors
+        saved = ctx.saved_tensors
+        k, v, bias, seg = saved[:4]
+        n = ctx.n_chunks
+        res = dict(q_chunks=list(saved[4:4 + n]), out_chunks=list(saved[4 + n:4 + 2 * n]),
+                   lse_chunks=list(saved[4 + 2 * n:4 + 3 * n]))
         group, rank, world = _resolve_group(ctx.axis_name)
-        dq, dk, dv = ring_backward(q, k, v, out, lse, dout.contiguous(), bias, seg, ctx.causal, group, rank,
-                                   world, ctx.layout)
+        dq, dk, dv = ring_backward(res, k, v, dout.contiguous(), bias, seg, ctx.causal, group, rank, world,
+                                   ctx.layout)
         return dq, dk, dv, None, None, None, None, None
 
 
@@ -147,36 +155,40 @@ def cast_f32_to_bf16(src, dst, stream=None):
 # ------------------------------------------------------------------------------------------------
 # ring drivers
 # ------------------------------------------------------------------------------------------------
-def _ring_exchange(send_tensors, recv_tensors, group, rank, world):
-    """One hop i -> i+1 of every tensor in the list (lax.ppermute of the reference)."""
-    nxt = dist.get_global_rank(group, (rank + 1) % world) if group is not dist.group.WORLD else (rank + 1) % world
-    prv = dist.get_global_rank(group, (rank - 1) % world) if group is not dist.group.WORLD else (rank - 1) % world
-    ops = []
-    for s, r in zip(send_tensors, recv_tensors):
-        ops.append(dist.P2POp(dist.isend, s, nxt, group))
-        ops.append(dist.P2POp(dist.irecv, r, prv, group))
-    return dist.batch_isend_irecv(ops)
+class CudaOps:
+    """The injected step functions of ring_exec: thin calls into liblwm_b200.so."""
+    fwd_step = staticmethod(fwd_step)
+    bwd_prep = staticmethod(bwd_prep)
+    bwd_step = staticmethod(bwd_step)
+    cast = staticmethod(cast_f32_to_bf16)
+
+    @staticmethod
+    def accumulate(acc, start, length, buf):
+        for b in range(acc.shape[0]):
+            dst = acc[b, start:start + length]
+            _lib.call("lwm_add_f32", _lib.ptr(dst), _lib.ptr(buf[b]), dst.numel(), _lib.stream_ptr())
 
 
 def ring_forward(q, k, v, bias, seg, causal, group, rank, world, layout="auto"):
+    """-> (out, residuals). world == 1 is the single-launch fast path (no carry buffers)."""
     B, Sq, H, D = q.shape
-    Sk = k.shape[1]
-    out = torch.empty_like(q)
-    lse = torch.empty((B, H, Sq), dtype=torch.float32, device=q.device)
     if world == 1:
+        out = torch.empty_like(q)
+        lse = torch.empty((B, H, Sq), dtype=torch.float32, device=q.device)
         fwd_step(q, k, v, out, lse, None, None, None, 0, 0, causal, bias, seg, True, True)
-        return out, lse
-    plan = rs.make_plan(world, rank, Sq, Sk, causal, layout)
-    return rs.run_forward(plan, q, k, v, out, lse, bias, seg, causal, group, rank, world, fwd_step, _ring_exchange)
+        return out, dict(q_chunks=[q], out_chunks=[out], lse_chunks=[lse])
+    plan = rs.make_plan(world, rank, Sq, k.shape[1], causal, layout)
+    return rx.run_forward(plan, q, k, v, bias, seg, causal, group, CudaOps)
 
 
-def ring_backward(q, k, v, out, lse, dout, bias, seg, causal, group, rank, world, layout="auto"):
-    B, Sq, H, D = q.shape
-    Sk = k.shape[1]
-    dev = q.device
-    delta = torch.empty((B, H, Sq), dtype=torch.float32, device=dev)
-    bwd_prep(out, dout, delta)
+def ring_backward(res, k, v, dout, bias, seg, causal, group, rank, world, layout="auto"):
+    B, Sk, H, D = k.shape
+    dev = k.device
     if world == 1:
+        q, out, lse = res["q_chunks"][0], res["out_chunks"][0], res["lse_chunks"][0]
+        Sq = q.shape[1]
+        delta = torch.empty((B, H, Sq), dtype=torch.float32, device=dev)
+        bwd_prep(out, dout, delta)
         dq_acc = torch.zeros((B, Sq, H, D), dtype=torch.float32, device=dev)
         dk_acc = torch.zeros((B, Sk, H, D), dtype=torch.float32, device=dev)
         dv_acc = torch.zeros((B, Sk, H, D), dtype=torch.float32, device=dev)
@@ -186,6 +198,5 @@ def ring_backward(q, k, v, out, lse, dout, bias, seg, causal, group, rank, world
         cast_f32_to_bf16(dk_acc, dk)
         cast_f32_to_bf16(dv_acc, dv)
         return dq, dk, dv
-    plan = rs.make_plan(world, rank, Sq, Sk, causal, layout)
-    return rs.run_backward(plan, q, k, v, dout, lse, delta, bias, seg, causal, group, rank, world, bwd_step,
-                           cast_f32_to_bf16, _ring_exchange)
+    plan = rs.make_plan(world, rank, dout.shape[1], Sk, causal, layout)
+    return rx.run_backward(plan, res, k, v, dout, bias, seg, causal, group, CudaOps)

@@ -15,6 +15,7 @@
 #include <cstdlib>
 #include <vector>
 #include <cmath>
+#include <cuda_fp16.h>
 #include "../lwm_b200/csrc/ptx.cuh"
 #include "../lwm_b200/csrc/tmap.h"
 
@@ -23,6 +24,7 @@ using namespace lwm;
 struct ProbeParams {
   int a_mode;  // 0 smem K-major, 1 smem MN-major, 2 TMEM
   int b_mode;  // 0 smem K-major, 1 smem MN-major
+  int a_f16;   // 1: the A operand holds IEEE fp16 while B stays bf16 (mixed-format kind::f16 MMA)
 };
 
 __global__ void __launch_bounds__(160, 1)
@@ -79,7 +81,7 @@ probe_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   if (warp == 4 && lane_id() == 0) {
     mbar_wait(&bar_load, 0);
     tc_fence_after();
-    const uint32_t idesc = make_idesc_bf16(128, 128, pp.a_mode == 1, pp.b_mode == 1);
+    const uint32_t idesc = make_idesc(128, 128, pp.a_mode == 1, pp.b_mode == 1, pp.a_f16 ? kFmtF16 : kFmtBF16, kFmtBF16);
     const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB);
 #pragma unroll
     for (int ks = 0; ks < 8; ++ks) {
@@ -149,7 +151,6 @@ __global__ void oob_probe(const __grid_constant__ CUtensorMap tm, float* out) {
   }
 }
 
-static float bf16r(float x) { return __bfloat162float(__float2bfloat16(x)); }
 
 int main() {
   cudaSetDevice(0);
@@ -206,13 +207,31 @@ int main() {
 
   const int smem_bytes = 65536 + 1024;
   cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
-  int cases[5][2] = {{0, 0}, {0, 1}, {2, 1}, {1, 1}, {2, 0}};
+  // fp16 copies of A (same logical values) for the mixed-format cases
+  std::vector<__half> hA_k16(M * K), hA_mn16(K * M);
+  for (int m = 0; m < M; ++m)
+    for (int k = 0; k < K; ++k) {
+      hA_k16[m * K + k] = __float2half(A[m * K + k]);
+      hA_mn16[k * M + m] = __float2half(A[m * K + k]);
+    }
+  __nv_bfloat16 *dA_k16, *dA_mn16;
+  cudaMalloc(&dA_k16, M * K * 2); cudaMalloc(&dA_mn16, M * K * 2);
+  cudaMemcpy(dA_k16, hA_k16.data(), M * K * 2, cudaMemcpyHostToDevice);
+  cudaMemcpy(dA_mn16, hA_mn16.data(), M * K * 2, cudaMemcpyHostToDevice);
+  CUtensorMap tA_k16 = mk(dA_k16), tA_mn16 = mk(dA_mn16);
+  int cases[9][3] = {{0, 0, 0}, {0, 1, 0}, {2, 1, 0}, {1, 1, 0}, {2, 0, 0}, {2, 1, 1}, {0, 1, 1}, {1, 1, 1}, {0, 0, 1}};
   int fails = 0;
-  for (int c = 0; c < 5; ++c) {
-    ProbeParams pp{cases[c][0], cases[c][1]};
+  for (int c = 0; c < 9; ++c) {
+    ProbeParams pp{cases[c][0], cases[c][1], cases[c][2]};
+    if (pp.a_f16) {
+      cudaMemset(dD, 0xff, M * N * 4);
+      probe_kernel<<<1, 160, smem_bytes>>>(pp.a_mode == 1 ? tA_mn16 : tA_k16, pp.b_mode == 1 ? tB_mn : tB_k, dA_k16,
+                                           dD, pp);
+    } else {
     cudaMemset(dD, 0xff, M * N * 4);
     probe_kernel<<<1, 160, smem_bytes>>>(pp.a_mode == 1 ? tA_mn : tA_k, pp.b_mode == 1 ? tB_mn : tB_k, dA_k,
                                          dD, pp);
+    }
     cudaError_t e = cudaDeviceSynchronize();
     std::vector<float> out(M * N);
     cudaMemcpy(out.data(), dD, M * N * 4, cudaMemcpyDeviceToHost);
@@ -223,8 +242,8 @@ int main() {
       if (!(d <= 1e-3)) ++bad;
       if (d > maxerr || d != d) maxerr = d;
     }
-    printf("case %d (a_mode=%d b_mode=%d): cuda=%s bad=%d/%d maxerr=%g  D[0][0..3]=%g %g %g %g ref=%g %g %g %g\n",
-           c, pp.a_mode, pp.b_mode, cudaGetErrorString(e), bad, M * N, maxerr, out[0], out[1], out[2], out[3],
+    printf("case %d (a_mode=%d b_mode=%d a_f16=%d): cuda=%s bad=%d/%d maxerr=%g  D[0][0..3]=%g %g %g %g ref=%g %g %g %g\n",
+           c, pp.a_mode, pp.b_mode, pp.a_f16, cudaGetErrorString(e), bad, M * N, maxerr, out[0], out[1], out[2], out[3],
            ref[0], ref[1], ref[2], ref[3]);
     if (bad || e != cudaSuccess) ++fails;
     if (e != cudaSuccess) { printf("sticky error, abort\n"); return 1; }
