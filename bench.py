@@ -1,0 +1,341 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the lwm_b200 hot paths (see BASELINE.json / DESIGN.md §Measurement).
+
+Workload (config.workload): ring attention forward+backward of ONE LWM-7B layer
+(H=32, D=128, hidden 4096, B=1, causal) at S=131072 tokens, bf16 in / fp32 accumulate, sequence
+sharded over N GPUs (N=1: the whole 128K sequence on one B200). A "step" is one forward+backward
+pass of that layer's attention through the public `ringattention` op. STRONG scaling: total
+work is fixed as N grows.
+
+  value   tokens/s of the attention path of a 32-layer 7B model = S / (32 * t_step), inputs resident
+          in HBM, device-timed (CUDA events, barrier + synchronize on both sides, max over ranks)
+  e2e     same metric through the same public op with HOST (pinned) q/k/v/dout: H2D copies of the
+          inputs and D2H copies of out/dq/dk/dv inside the timed region
+  roofline   tensor-bound: algorithmic causal FLOPs of the dominant kernel (attn_bwd_kernel) per
+          launch / its CUDA-event duration, against the measured cuBLAS bf16 peak
+  cpu_baseline / --impl reference   the CPU restatement of the reference algorithm (oracle/),
+          timed on the host cores on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+S_TOTAL = 131072
+H, D, LAYERS = 32, 128, 32
+METRIC = "ring_attn_fwd_bwd_tokens_per_s_attention_only_7B_128K"
+UNIT = "tokens/s"
+
+
+def f_fwd(S):
+    """algorithmic causal forward FLOPs of one layer: 4*B*H*D*S(S+1)/2."""
+    return 4.0 * H * D * S * (S + 1) / 2.0
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(burst=float(d["bf16_tflops"]), sustained=float(d.get("bf16_tflops_sustained", d["bf16_tflops"])),
+                    hbm=float(d["hbm_gbs"]), source="MEASURED_PEAKS.json")
+    return dict(burst=1590.0, sustained=1400.0, hbm=6650.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index = index
+        self.samples = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            pass
+        clocks, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            parts = [x.strip() for x in s.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                clocks.append(float(parts[0]))
+                mx = float(parts[1])
+            except ValueError:
+                continue
+            for n, val in zip(names, parts[2:6]):
+                if val.lower().startswith("active"):
+                    reasons.add(n)
+        clocks.sort()
+        med = clocks[len(clocks) // 2] if clocks else None
+        return {"sm_mhz": med, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(clocks)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU restatement timed on the host cores (cpu_baseline and --impl reference)
+# ------------------------------------------------------------------------------------------------
+def cpu_sample_step(S, rows, heads, chunk=1024):
+    """Blockwise online-softmax forward + recompute backward for the LAST
+    `rows` query rows of an S-token causal sequence and `heads` heads, fp32, torch CPU matmuls.
+    Returns (seconds, flops)."""
+    import torch
+    from oracle import ring_blockwise as rb
+    g = torch.Generator().manual_seed(0)
+    q = torch.randn(1, rows, heads, D, generator=g)
+    k = torch.randn(1, S, heads, D, generator=g)
+    v = torch.randn(1, S, heads, D, generator=g)
+    do = torch.randn(1, rows, heads, D, generator=g)
+    t0 = time.perf_counter()
+    rb.torch_blockwise_fwd_bwd(q, k, v, do, q_pos0=S - rows, chunk=chunk)
+    dt = time.perf_counter() - t0
+    # full (not causal-halved) tiles except the diagonal chunk: count exact visible pairs
+    vis = sum(min(S, (S - rows) + i + 1) for i in range(rows))
+    flops = 3.5 * 4.0 * heads * D * vis
+    return dt, flops
+
+
+def run_reference_arm(args, rank):
+    """`--impl reference`: the reference's own (CPU) algorithm for this path, restated in oracle/
+    (the un-vendored JAX package cannot be installed offline — DESIGN.md), all host threads."""
+    if rank != 0:
+        return
+    import torch
+    cores = len(os.sched_getaffinity(0))
+    torch.set_num_threads(cores)
+    rows, heads = 2048, 2
+    times, flops = [], 0.0
+    for i in range(args.warmup + args.steps):
+        dt, flops = cpu_sample_step(S_TOTAL, rows, heads)
+        if i >= args.warmup:
+            times.append(dt)
+    t = sum(times) / len(times)
+    full = 3.5 * f_fwd(S_TOTAL)
+    t_layer = t * full / flops                      # extrapolated time of one whole layer
+    value = S_TOTAL / (LAYERS * t_layer)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "LWM-7B attention fwd+bwd, S=131072, B=1, H=32, D=128, causal",
+                   "note": "CPU restatement of the reference algorithm (oracle/ring_blockwise.py); the JAX "
+                           "reference cannot be installed offline"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": "last %d query rows x %d head of the 128K causal problem per step, fwd+bwd, "
+                                   "extrapolated by FLOPs (x%.0f) to one layer" % (rows, heads, full / flops)},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "cpu_gflops": flops / t / 1e9,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="lwm_b200")
+    ap.add_argument("--seq", type=int, default=S_TOTAL, help="(debug) override the total sequence length")
+    ap.add_argument("--layout", default="auto")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-vqgan", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference_arm(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from lwm_b200 import ringattention as ra
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: lwm_b200 has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    S = args.seq
+    assert S % world == 0
+    Sl = S // world
+    W, K = max(args.warmup, 3), args.steps
+    peaks = load_peaks()
+
+    g = torch.Generator(device="cpu").manual_seed(1234 + rank)
+
+    def mk():
+        return torch.randn(1, Sl, H, D, generator=g, dtype=torch.float32).to(torch.bfloat16)
+    hq, hk, hv, hdo = [mk().pin_memory() for _ in range(4)]
+    q, k, v, do = [t.to(dev) for t in (hq, hk, hv, hdo)]
+    kwargs = dict(axis_name="sp", float32_logits=True, cache_idx=None,
+                  blockwise_kwargs=dict(causal_block_size=1, deterministic=True, dropout_rng=None, attn_pdrop=0.0,
+                                        query_chunk_size=1024, key_chunk_size=1024, dtype=torch.bfloat16,
+                                        policy=None, precision=None, prevent_cse=True), layout=args.layout)
+
+    ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
+    kern_ms = {"fwd": [], "bwd": []}
+
+    def step():
+        qq, kk, vv = [t.detach().requires_grad_(True) for t in (q, k, v)]
+        out = ra.ringattention(qq, kk, vv, None, None, **kwargs)
+        out.backward(do)
+        return out, qq.grad, kk.grad, vv.grad
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(W):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    t0, t1 = ev(), ev()
+    barrier()
+    t0.record()
+    for _ in range(K):
+        step()
+    t1.record()
+    barrier()
+    ms = t0.elapsed_time(t1) / K
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        tm = torch.tensor([ms], device=dev)
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        ms = float(tm.item())
+    launches_per_step = 6 if world == 1 else None
+
+    # ---- dominant-kernel timing (single GPU): the raw fwd / bwd tile kernels, CUDA events on their stream
+    roof = None
+    if world == 1:
+        out = torch.empty_like(q)
+        lse = torch.empty(1, H, Sl, dtype=torch.float32, device=dev)
+        delta = torch.empty_like(lse)
+        dq = torch.zeros(1, Sl, H, D, dtype=torch.float32, device=dev)
+        dk = torch.zeros_like(dq)
+        dv = torch.zeros_like(dq)
+        ra.fwd_step(q, k, v, out, lse, None, None, None, 0, 0, True, None, None, True, True)
+        ra.bwd_prep(out, do, delta)
+        for name, fn in (("fwd", lambda: ra.fwd_step(q, k, v, out, lse, None, None, None, 0, 0, True, None, None,
+                                                     True, True)),
+                         ("bwd", lambda: ra.bwd_step(q, k, v, do, lse, delta, dq, dk, dv, 0, 0, True, None, None))):
+            fn()
+            torch.cuda.synchronize()
+            a, b2 = ev(), ev()
+            a.record()
+            for _ in range(3):
+                fn()
+            b2.record()
+            torch.cuda.synchronize()
+            kern_ms[name] = a.elapsed_time(b2) / 3
+        del dq, dk, dv
+        fl_bwd = 2.5 * f_fwd(S)
+        ach = fl_bwd / (kern_ms["bwd"] * 1e-3) / 1e12
+        roof = {"bound": "tensor", "kernel": "attn_bwd_kernel", "achieved": ach, "peak": peaks["sustained"],
+                "unit": "TFLOP/s", "frac": ach / peaks["sustained"], "traffic": None,
+                "peak_source": peaks["source"] + " bf16_tflops_sustained (kernel timed inside a long step); burst=%.1f"
+                % peaks["burst"],
+                "fwd_kernel": {"achieved": f_fwd(S) / (kern_ms["fwd"] * 1e-3) / 1e12,
+                               "frac": f_fwd(S) / (kern_ms["fwd"] * 1e-3) / 1e12 / peaks["sustained"],
+                               "ms": kern_ms["fwd"]},
+                "bwd_kernel_ms": kern_ms["bwd"], "share_of_step": (kern_ms["bwd"]) / ms}
+
+    # ---- end-to-end through the public op with host buffers
+    hout = torch.empty_like(hq).pin_memory()
+    hdq, hdk, hdv = [torch.empty_like(hq).pin_memory() for _ in range(3)]
+
+    def e2e_step():
+        qd = hq.to(dev, non_blocking=True).requires_grad_(True)
+        kd = hk.to(dev, non_blocking=True).requires_grad_(True)
+        vd = hv.to(dev, non_blocking=True).requires_grad_(True)
+        dod = hdo.to(dev, non_blocking=True)
+        o = ra.ringattention(qd, kd, vd, None, None, **kwargs)
+        o.backward(dod)
+        hout.copy_(o.detach(), non_blocking=True)
+        hdq.copy_(qd.grad, non_blocking=True)
+        hdk.copy_(kd.grad, non_blocking=True)
+        hdv.copy_(vd.grad, non_blocking=True)
+
+    e2e_step()
+    barrier()
+    a, b2 = ev(), ev()
+    a.record()
+    n_e2e = max(2, min(K, 3))
+    for _ in range(n_e2e):
+        e2e_step()
+    b2.record()
+    barrier()
+    ms_e2e = a.elapsed_time(b2) / n_e2e
+    if world > 1:
+        tm = torch.tensor([ms_e2e], device=dev)
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        ms_e2e = float(tm.item())
+    bytes_in = 4 * hq.numel() * 2
+    bytes_out = 4 * hq.numel() * 2
+
+    if rank == 0:
+        total_flops = 3.5 * f_fwd(S)
+        line = {
+            "metric": METRIC, "value": S / (LAYERS * ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K,
+            "warmup": W, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "LWM-7B ring attention fwd+bwd, one layer, S=%d B=1 H=32 D=128 causal, "
+                                   "sequence-sharded over %d GPU(s)" % (S, world),
+                       "layout": args.layout, "l2": "inputs (>=1 GiB per tensor at N=1) larger than the 126 MB L2",
+                       "tokens_per_s_definition": "S / (32 layers * t_step), attention only"},
+            "tflops_per_gpu": total_flops / (ms * 1e-3) / 1e12 / world,
+            "frac_of_bf16_peak_per_gpu": total_flops / (ms * 1e-3) / 1e12 / world / peaks["sustained"],
+            "e2e": {"value": S / (LAYERS * ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
+                    "h2d_bytes_per_step": bytes_in, "d2h_bytes_per_step": bytes_out},
+            "gpu_launches": (launches_per_step * K) if launches_per_step else None,
+            "clocks": clocks,
+        }
+        if roof:
+            line["roofline"] = roof
+        if not args.no_cpu_baseline:
+            cores = len(os.sched_getaffinity(0))
+            torch.set_num_threads(cores)
+            dt, fl = cpu_sample_step(8192, 8192, 32, chunk=1024)
+            line["cpu_baseline"] = {
+                "value": 8192 / (LAYERS * dt), "unit": UNIT, "cores": cores, "kind": "port",
+                "gflops": fl / dt / 1e9,
+                "sample": "oracle blockwise fwd+bwd (torch CPU fp32) of one full layer at S=8192 (32 heads, causal); "
+                          "%.1f s of CPU work; tokens/s = 8192 / (32 layers * t)" % dt}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

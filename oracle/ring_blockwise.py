@@ -140,3 +140,61 @@ def ring_attention_bwd(q_shards, k_shards, v_shards, outs, residuals, douts, att
     dk = [held[r][2] for r in range(P)]
     dv = [held[r][3] for r in range(P)]
     return dq, dk, dv
+
+
+def torch_blockwise_fwd_bwd(q, k, v, dout, q_pos0=0, chunk=1024):
+    """Same blockwise algorithm (online-softmax forward with (numerator, denominator, max) carry, then
+    the recompute backward of Appendix A) for ONE device holding q rows [q_pos0, q_pos0+Sq) and all
+    keys, written with torch CPU fp32 matmuls so that it can use every host core. Used by bench.py
+    to time the reference algorithm on the host (cpu_baseline / --impl reference)."""
+    import torch
+    B, Sq, H, D = q.shape
+    Sk = k.shape[1]
+    scale = 1.0 / float(np.sqrt(D))
+    qh, kh, vh, gh = [x.permute(0, 2, 1, 3).contiguous().float() for x in (q, k, v, dout)]  # [B,H,S,D]
+    num = torch.zeros_like(qh)
+    den = torch.zeros(B, H, Sq)
+    mx = torch.full((B, H, Sq), -float("inf"))
+    neg = float(np.finfo(np.float32).min)
+    qc = min(chunk, Sq)
+    for i in range(0, Sq, qc):
+        qi = qh[:, :, i:i + qc]
+        qpos = q_pos0 + i + torch.arange(qi.shape[2])
+        for j in range(0, Sk, chunk):
+            if j > q_pos0 + i + qc - 1:
+                break                                   # tile entirely above the diagonal: skipped
+            kj, vj = kh[:, :, j:j + chunk], vh[:, :, j:j + chunk]
+            s = torch.matmul(qi, kj.transpose(-1, -2)) * scale
+            kpos = j + torch.arange(kj.shape[2])
+            if j + chunk - 1 > q_pos0 + i:
+                s = s + (qpos[:, None] < kpos[None, :]).float() * neg
+            m_new = torch.maximum(mx[:, :, i:i + qc], s.max(-1).values)
+            p = torch.exp(s - m_new[..., None])
+            c = torch.exp(mx[:, :, i:i + qc] - m_new)
+            num[:, :, i:i + qc] = num[:, :, i:i + qc] * c[..., None] + torch.matmul(p, vj)
+            den[:, :, i:i + qc] = den[:, :, i:i + qc] * c + p.sum(-1)
+            mx[:, :, i:i + qc] = m_new
+    out = num / den[..., None]
+    dq = torch.zeros_like(qh)
+    dk = torch.zeros_like(kh)
+    dv = torch.zeros_like(vh)
+    delta = (gh * out).sum(-1)
+    for i in range(0, Sq, qc):
+        qi, gi = qh[:, :, i:i + qc], gh[:, :, i:i + qc]
+        qpos = q_pos0 + i + torch.arange(qi.shape[2])
+        for j in range(0, Sk, chunk):
+            if j > q_pos0 + i + qc - 1:
+                break
+            kj, vj = kh[:, :, j:j + chunk], vh[:, :, j:j + chunk]
+            s = torch.matmul(qi, kj.transpose(-1, -2)) * scale
+            kpos = j + torch.arange(kj.shape[2])
+            if j + chunk - 1 > q_pos0 + i:
+                s = s + (qpos[:, None] < kpos[None, :]).float() * neg
+            p = torch.exp(s - mx[:, :, i:i + qc, None]) / den[:, :, i:i + qc, None]
+            dv[:, :, j:j + chunk] += torch.matmul(p.transpose(-1, -2), gi)
+            dp = torch.matmul(gi, vj.transpose(-1, -2))
+            dl = (dp - delta[:, :, i:i + qc, None]) * p
+            dq[:, :, i:i + qc] += torch.matmul(dl, kj) * scale
+            dk[:, :, j:j + chunk] += torch.matmul(dl.transpose(-1, -2), qi) * scale
+    back = lambda x: x.permute(0, 2, 1, 3)
+    return back(out), back(dq), back(dk), back(dv)
