@@ -1,0 +1,331 @@
+// HBM-bound pieces of the VQGAN tokenizer (lwm/vqgan.py), NHWC fp32 activations:
+//   lwm_vq_gn_stats   per-(sample, group) sum and sum of squares for flax nn.GroupNorm() (32 groups,
+//                     statistics over H,W,C/32 — vqgan.py:161,181,251,254)
+//   lwm_vq_prep       GroupNorm-apply + SiLU (vqgan.py:251-256) and/or nearest 2x upsampling
+//                     (vqgan.py:312-316) fused with the conversion of the activation into the
+//                     tensor-core operand planes (bf16 hi, bf16 lo = x - hi) the conv kernel reads by TMA
+//   lwm_vq_conv_cin3  direct 3x3 SAME conv for the 3-channel input layer (Encoder conv_in,
+//                     vqgan.py:155): 27 MACs per output, far too thin for the tensor pipe
+//   lwm_vq_argmin     VectorQuantizer nearest-code search (vqgan.py:207-215), bit-exact fp32 order
+//   lwm_vq_gather     codebook lookup for decode (vqgan.py:193-195)
+#include "ptx.cuh"
+#include "capi_internal.h"
+
+namespace lwm {
+
+// ------------------------------------------------------------------------------------------------
+// GroupNorm statistics: stats[n][g] = (sum, sumsq) in double (atomics; zeroed by the caller).
+// Thread t owns channel quad (t % (C/4)) and strides over pixels, so a warp reads whole 128 B lines.
+// ------------------------------------------------------------------------------------------------
+__global__ void gn_stats_kernel(const float* __restrict__ x, double* __restrict__ stats, int HW, int C,
+                                int groups, int pix_per_block) {
+  extern __shared__ float s_part[];  // [groups][2]
+  const int n = blockIdx.y;
+  const int quads = C / 4;
+  const int cpg = C / groups;
+  for (int i = threadIdx.x; i < groups * 2; i += blockDim.x) s_part[i] = 0.f;
+  __syncthreads();
+  const int q = threadIdx.x % quads;
+  const int prow = threadIdx.x / quads;
+  const int prows = blockDim.x / quads;
+  const int p0 = blockIdx.x * pix_per_block;
+  const int p1 = min(HW, p0 + pix_per_block);
+  float s = 0.f, ss = 0.f;
+  if (prow < prows) {
+    const float4* base = reinterpret_cast<const float4*>(x + (size_t)n * HW * C) + q;
+    for (int p = p0 + prow; p < p1; p += prows) {
+      const float4 v = base[(size_t)p * quads];
+      s += (v.x + v.y) + (v.z + v.w);
+      ss += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+    }
+  }
+  const int g = (q * 4) / cpg;
+  atomicAdd(&s_part[2 * g], s);
+  atomicAdd(&s_part[2 * g + 1], ss);
+  __syncthreads();
+  for (int i = threadIdx.x; i < groups * 2; i += blockDim.x)
+    atomicAdd(&stats[((size_t)n * groups) * 2 + i], (double)s_part[i]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// prep: y = [silu(gn(x))] at (h>>up, w>>up); hi = bf16(y); lo = bf16(y - hi). Output planes have
+// C_pad >= C channels (multiple of 64 for the conv's 128-byte TMA rows); padding channels are zero.
+// ------------------------------------------------------------------------------------------------
+__global__ void prep_kernel(const float* __restrict__ x, const double* __restrict__ stats,
+                            const float* __restrict__ gamma, const float* __restrict__ beta,
+                            __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int N, int H, int W,
+                            int C, int C_pad, int groups, int up, float eps, int write_lo) {
+  const int Ho = H << up, Wo = W << up;
+  const int quads = C_pad / 4;
+  const size_t total = (size_t)N * Ho * Wo * quads;
+  const int cpg = C / groups;
+  const double inv_cnt = 1.0 / ((double)H * W * cpg);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int q = int(i % quads);
+    size_t pix = i / quads;
+    const int wo = int(pix % Wo);
+    pix /= Wo;
+    const int ho = int(pix % Ho);
+    const int n = int(pix / Ho);
+    const int c = q * 4;
+    float y[4] = {0.f, 0.f, 0.f, 0.f};
+    if (c < C) {
+      const float4 v = *reinterpret_cast<const float4*>(x + (((size_t)n * H + (ho >> up)) * W + (wo >> up)) * C + c);
+      y[0] = v.x; y[1] = v.y; y[2] = v.z; y[3] = v.w;
+      if (stats) {
+        const int g = c / cpg;
+        const double sum = stats[((size_t)n * groups + g) * 2], sumsq = stats[((size_t)n * groups + g) * 2 + 1];
+        const float mean = float(sum * inv_cnt);
+        float var = float(sumsq * inv_cnt) - mean * mean;   // flax fast variance, clamped at 0
+        var = fmaxf(var, 0.f);
+        const float rstd = rsqrtf(var + eps);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float t = (y[e] - mean) * rstd * gamma[c + e] + beta[c + e];
+          y[e] = t / (1.0f + __expf(-t));   // silu = t * sigmoid(t)
+        }
+      }
+    }
+    __nv_bfloat16 h4[4], l4[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      h4[e] = __float2bfloat16_rn(y[e]);
+      l4[e] = __float2bfloat16_rn(y[e] - __bfloat162float(h4[e]));
+    }
+    const size_t o = (((size_t)n * Ho + ho) * Wo + wo) * C_pad + c;
+    *reinterpret_cast<uint2*>(hi + o) = *reinterpret_cast<const uint2*>(h4);
+    if (write_lo) *reinterpret_cast<uint2*>(lo + o) = *reinterpret_cast<const uint2*>(l4);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// direct conv, Cin = 3, 3x3 SAME, Cout multiple of 32: block = 8x8 output pixels x all Cout,
+// weights [27][Cout] in smem, each thread = one pixel x 32 output channels.
+// ------------------------------------------------------------------------------------------------
+__global__ void conv_cin3_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                 const float* __restrict__ bias, float* __restrict__ y, int N, int H, int W,
+                                 int Cout) {
+  extern __shared__ float s_w[];  // [27][Cout] then input patch [10][10][3]
+  float* s_in = s_w + 27 * Cout;
+  const int tiles_w = W / 8;
+  const int tw = blockIdx.x % tiles_w, th = blockIdx.x / tiles_w, n = blockIdx.y;
+  for (int i = threadIdx.x; i < 27 * Cout; i += blockDim.x) s_w[i] = w[i];
+  for (int i = threadIdx.x; i < 300; i += blockDim.x) {
+    const int c = i % 3, px = (i / 3) % 10, py = i / 30;
+    const int gy = th * 8 + py - 1, gx = tw * 8 + px - 1;
+    s_in[i] = (gy >= 0 && gy < H && gx >= 0 && gx < W) ? x[(((size_t)n * H + gy) * W + gx) * 3 + c] : 0.f;
+  }
+  __syncthreads();
+  const int groups_c = Cout / 32;
+  const int pix = threadIdx.x / groups_c, cg = threadIdx.x % groups_c;  // blockDim = 64 * groups_c
+  const int py = pix / 8, px = pix % 8;
+  float acc[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) acc[j] = bias[cg * 32 + j];
+#pragma unroll
+  for (int t = 0; t < 27; ++t) {
+    const int kh = t / 9, kw = (t / 3) % 3, c = t % 3;   // HWIO order: (kh, kw, cin)
+    const float a = s_in[((py + kh) * 10 + (px + kw)) * 3 + c];
+    const float* wr = s_w + t * Cout + cg * 32;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) acc[j] = fmaf(a, wr[j], acc[j]);
+  }
+  float* dst = y + (((size_t)n * H + th * 8 + py) * W + tw * 8 + px) * Cout + cg * 32;
+#pragma unroll
+  for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// VectorQuantizer: idx[b] = argmin_n ((sum z^2 + sum e_n^2) - 2 z.e_n), first index on ties.
+// Arithmetic order pinned to oracle/vqgan_ref.py::vq_distances_f32: sequential over d, multiply and
+// add rounded separately (__fmul_rn/__fadd_rn forbid FMA contraction) => bit-exact indices.
+// Block = 128 threads, 16 rows of z; the codebook streams through in tiles of 128 codes
+// (thread = one code held in registers), rows broadcast from shared memory.
+// ------------------------------------------------------------------------------------------------
+constexpr int kVqRows = 16;
+constexpr int kVqDim = 64;
+
+__global__ void __launch_bounds__(128)
+vq_argmin_kernel(const float* __restrict__ z, const float* __restrict__ emb, int* __restrict__ idx,
+                 float* __restrict__ zq_st, int N, int n_e) {
+  __shared__ float s_z[kVqRows][kVqDim];
+  __shared__ float s_zz[kVqRows];
+  __shared__ float s_best_d[kVqRows][4];
+  __shared__ int s_best_i[kVqRows][4];
+  const int row0 = blockIdx.x * kVqRows;
+  const int nrows = min(kVqRows, N - row0);
+  for (int i = threadIdx.x; i < kVqRows * kVqDim; i += blockDim.x) {
+    const int r = i / kVqDim, d = i % kVqDim;
+    s_z[r][d] = (r < nrows) ? z[(size_t)(row0 + r) * kVqDim + d] : 0.f;
+  }
+  __syncthreads();
+  if (threadIdx.x < kVqRows) {
+    float a = 0.f;
+    for (int d = 0; d < kVqDim; ++d) a = __fadd_rn(a, __fmul_rn(s_z[threadIdx.x][d], s_z[threadIdx.x][d]));
+    s_zz[threadIdx.x] = a;
+  }
+  __syncthreads();
+  float best_d[kVqRows];
+  int best_i[kVqRows];
+#pragma unroll
+  for (int r = 0; r < kVqRows; ++r) {
+    best_d[r] = INFINITY;
+    best_i[r] = 0x7fffffff;
+  }
+  for (int c0 = 0; c0 < n_e; c0 += 128) {
+    const int code = c0 + threadIdx.x;
+    if (code < n_e) {
+      float e[kVqDim];
+      const float4* src = reinterpret_cast<const float4*>(emb + (size_t)code * kVqDim);
+#pragma unroll
+      for (int d4 = 0; d4 < kVqDim / 4; ++d4) {
+        const float4 v = src[d4];
+        e[4 * d4] = v.x; e[4 * d4 + 1] = v.y; e[4 * d4 + 2] = v.z; e[4 * d4 + 3] = v.w;
+      }
+      float ee = 0.f;
+#pragma unroll
+      for (int d = 0; d < kVqDim; ++d) ee = __fadd_rn(ee, __fmul_rn(e[d], e[d]));
+#pragma unroll
+      for (int r = 0; r < kVqRows; ++r) {
+        float dot = 0.f;
+#pragma unroll
+        for (int d = 0; d < kVqDim; ++d) dot = __fadd_rn(dot, __fmul_rn(s_z[r][d], e[d]));
+        const float dist = __fadd_rn(__fadd_rn(s_zz[r], ee), -__fmul_rn(2.0f, dot));
+        if (dist < best_d[r]) {   // codes are visited in ascending order: strict < keeps the first index
+          best_d[r] = dist;
+          best_i[r] = code;
+        }
+      }
+    }
+  }
+  // reduce across the 128 threads: min distance, then smallest index
+  const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+#pragma unroll
+  for (int r = 0; r < kVqRows; ++r) {
+    float d = best_d[r];
+    int i = best_i[r];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float d2 = __shfl_xor_sync(0xffffffffu, d, o);
+      const int i2 = __shfl_xor_sync(0xffffffffu, i, o);
+      if (d2 < d || (d2 == d && i2 < i)) {
+        d = d2;
+        i = i2;
+      }
+    }
+    if (lane == 0) {
+      s_best_d[r][wp] = d;
+      s_best_i[r][wp] = i;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < nrows) {
+    const int r = threadIdx.x;
+    float d = s_best_d[r][0];
+    int i = s_best_i[r][0];
+    for (int k = 1; k < 4; ++k)
+      if (s_best_d[r][k] < d || (s_best_d[r][k] == d && s_best_i[r][k] < i)) {
+        d = s_best_d[r][k];
+        i = s_best_i[r][k];
+      }
+    idx[row0 + r] = i;
+    s_best_i[r][0] = i;
+  }
+  __syncthreads();
+  if (zq_st) {  // straight-through value z + (e[idx] - z), rounded like the reference (vqgan.py:215)
+    for (int t = threadIdx.x; t < nrows * kVqDim; t += blockDim.x) {
+      const int r = t / kVqDim, d = t % kVqDim;
+      const float zv = s_z[r][d];
+      const float ev = emb[(size_t)s_best_i[r][0] * kVqDim + d];
+      zq_st[(size_t)(row0 + r) * kVqDim + d] = __fadd_rn(zv, __fadd_rn(ev, -zv));
+    }
+  }
+}
+
+__global__ void vq_gather_kernel(const int* __restrict__ idx, const float4* __restrict__ emb, float4* __restrict__ out,
+                                 long long N, int quads, int n_e) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N * quads;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / quads;
+    int c = idx[r];
+    c = min(max(c, 0), n_e - 1);
+    out[i] = emb[(long long)c * quads + (i % quads)];
+  }
+}
+
+}  // namespace lwm
+
+using namespace lwm;
+
+extern "C" int lwm_vq_gn_stats(const float* x, double* stats, int N, int H, int W, int C, int groups, void* stream) {
+  if (!lwm_check_device()) return LWM_ERR_DEVICE;
+  if (!x || !stats) return lwm_fail(LWM_ERR_ARG, "vq_gn_stats: null pointer");
+  if (C % groups || (C / groups) % 4 || C % 4) return lwm_fail(LWM_ERR_SHAPE, "vq_gn_stats: C/groups must be a multiple of 4");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (cudaMemsetAsync(stats, 0, sizeof(double) * 2 * N * groups, st) != cudaSuccess)
+    return lwm_fail(LWM_ERR_CUDA, "vq_gn_stats: memset failed");
+  const int quads = C / 4;
+  int threads = ((512 / quads) > 0 ? (512 / quads) : 1) * quads;   // whole pixel rows per block
+  if (threads > 1024) threads = quads;
+  const int HW = H * W;
+  int ppb = 256;
+  while ((HW + ppb - 1) / ppb * N < 296 && ppb > 16) ppb /= 2;   // >= 2 blocks per SM
+  dim3 grid((HW + ppb - 1) / ppb, N);
+  gn_stats_kernel<<<grid, threads, groups * 2 * sizeof(float), st>>>(x, stats, HW, C, groups, ppb);
+  return lwm_check_launch("gn_stats_kernel");
+}
+
+extern "C" int lwm_vq_prep(const float* x, const double* gn_stats, const float* gamma, const float* beta, void* hi,
+                           void* lo, int N, int H, int W, int C, int C_pad, int groups, int upsample2x, float eps,
+                           void* stream) {
+  if (!lwm_check_device()) return LWM_ERR_DEVICE;
+  if (!x || !hi) return lwm_fail(LWM_ERR_ARG, "vq_prep: null pointer");
+  if (C % 4 || C_pad % 4 || C_pad < C) return lwm_fail(LWM_ERR_SHAPE, "vq_prep: C and C_pad must be multiples of 4");
+  if (gn_stats && (!gamma || !beta || C % groups || (C / groups) % 4))
+    return lwm_fail(LWM_ERR_SHAPE, "vq_prep: GroupNorm needs gamma/beta and C/groups % 4 == 0");
+  const size_t total = (size_t)N * (H << upsample2x) * (W << upsample2x) * (C_pad / 4);
+  const int threads = 256;
+  const size_t want = (total + threads - 1) / threads;
+  const unsigned blocks = unsigned(want < 148u * 32 ? want : 148u * 32);
+  prep_kernel<<<blocks, threads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      x, gn_stats, gamma, beta, reinterpret_cast<__nv_bfloat16*>(hi), reinterpret_cast<__nv_bfloat16*>(lo), N, H, W,
+      C, C_pad, groups, upsample2x ? 1 : 0, eps, lo != nullptr);
+  return lwm_check_launch("prep_kernel");
+}
+
+extern "C" int lwm_vq_conv_cin3(const float* x, const float* w_hwio, const float* bias, float* y, int N, int H, int W,
+                                int Cout, void* stream) {
+  if (!lwm_check_device()) return LWM_ERR_DEVICE;
+  if (!x || !w_hwio || !bias || !y) return lwm_fail(LWM_ERR_ARG, "vq_conv_cin3: null pointer");
+  if (H % 8 || W % 8 || Cout % 32 || Cout > 512) return lwm_fail(LWM_ERR_SHAPE, "vq_conv_cin3: H,W % 8, Cout % 32");
+  dim3 grid((H / 8) * (W / 8), N);
+  const int threads = 64 * (Cout / 32);
+  const size_t smem = (27 * Cout + 300) * sizeof(float);
+  conv_cin3_kernel<<<grid, threads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(x, w_hwio, bias, y, N, H, W, Cout);
+  return lwm_check_launch("conv_cin3_kernel");
+}
+
+extern "C" int lwm_vq_argmin(const float* z, const float* codebook, int* idx, float* zq_st, int N, int n_e, int e_dim,
+                             void* stream) {
+  if (!lwm_check_device()) return LWM_ERR_DEVICE;
+  if (!z || !codebook || !idx) return lwm_fail(LWM_ERR_ARG, "vq_argmin: null pointer");
+  if (e_dim != kVqDim) return lwm_fail(LWM_ERR_SHAPE, "vq_argmin: e_dim must be 64 (quantized_embed_dim, vqgan.py:72)");
+  if (N <= 0 || n_e <= 0) return lwm_fail(LWM_ERR_SHAPE, "vq_argmin: empty input");
+  vq_argmin_kernel<<<(N + kVqRows - 1) / kVqRows, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(z, codebook, idx,
+                                                                                                   zq_st, N, n_e);
+  return lwm_check_launch("vq_argmin_kernel");
+}
+
+extern "C" int lwm_vq_gather(const int* idx, const float* codebook, float* out, long long N, int n_e, int e_dim,
+                             void* stream) {
+  if (!lwm_check_device()) return LWM_ERR_DEVICE;
+  if (!idx || !codebook || !out) return lwm_fail(LWM_ERR_ARG, "vq_gather: null pointer");
+  if (e_dim % 4) return lwm_fail(LWM_ERR_SHAPE, "vq_gather: e_dim % 4");
+  if (N == 0) return LWM_OK;
+  const int quads = e_dim / 4;
+  const long long total = N * quads;
+  const unsigned blocks = unsigned((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+  vq_gather_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      idx, reinterpret_cast<const float4*>(codebook), reinterpret_cast<float4*>(out), N, quads, n_e);
+  return lwm_check_launch("vq_gather_kernel");
+}
