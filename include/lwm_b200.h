@@ -86,6 +86,38 @@ int lwm_cast_f32_to_bf16(const float* src, void* dst, long long n, void* stream)
 /* dst[i] += src[i] (fp32, n % 4 == 0): folds a dK/dV partial received from a peer into the owner's accumulator. */
 int lwm_add_f32(float* dst, const float* src, long long n, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * VQGAN tokenizer (lwm/vqgan.py:105-351). Activations are NHWC fp32 (flax layout and dtype).
+ *
+ * lwm_vq_gn_stats  (sum, sum of squares) per (sample, group) for flax nn.GroupNorm()
+ *                  (32 groups; vqgan.py:161,181,251,254); stats [N, groups, 2] float64, zeroed here.
+ * lwm_vq_prep      turns an activation into the conv kernel's tensor-core operand planes:
+ *                  y = silu(groupnorm(x)) when gn_stats != NULL (ResnetBlock, vqgan.py:251-256), else y = x;
+ *                  optional nearest 2x upsampling (Upsample, vqgan.py:312-316);
+ *                  hi = bf16(y) and, if lo != NULL, lo = bf16(y - hi); planes are [N,H',W',C_pad].
+ * lwm_vq_conv2d    flax nn.Conv as an implicit GEMM on tcgen05: ksize 1|3, stride 1 (SAME, pad=ksize/2) or
+ *                  the Downsample conv (stride 2, pad 0 on top/left, implicit zero bottom/right,
+ *                  vqgan.py:292-300). Weights pre-packed [taps][Cout_pad][C_pad] bf16 (hi / lo).
+ *                  n_pass 1 = bf16 operands; 3 = split-bf16 (hi+lo) operands, fp32-class accuracy.
+ *                  out = conv + bias (+ residual) (clamped to [-1,1] when clip, vqgan.py:141).
+ * lwm_vq_conv_cin3 Encoder conv_in (3 -> Cout, 3x3 SAME, vqgan.py:155) on the CUDA cores; w is HWIO.
+ * lwm_vq_argmin    VectorQuantizer (vqgan.py:207-215): idx = argmin_n (sum z^2 + sum e_n^2 - 2 z.e_n) with the
+ *                  first index on ties, fp32 with a pinned operation order (bit-exact vs oracle/vqgan_ref.py);
+ *                  zq_st (optional) = z + (e[idx] - z). workspace: 8 * N * 8 bytes.
+ * lwm_vq_gather    out[i] = codebook[idx[i]] (decode path, vqgan.py:193-195).
+ */
+int lwm_vq_gn_stats(const float* x, double* stats, int N, int H, int W, int C, int groups, void* stream);
+int lwm_vq_prep(const float* x, const double* gn_stats, const float* gamma, const float* beta, void* hi, void* lo,
+                int N, int H, int W, int C, int C_pad, int groups, int upsample2x, float eps, void* stream);
+int lwm_vq_conv2d(const void* a_hi, const void* a_lo, const void* w_hi, const void* w_lo, const float* bias,
+                  const float* residual, float* out, int N, int Hin, int Win, int Cpad, int Ho, int Wo, int Cout,
+                  int Cout_pad, int ksize, int stride, int pad, int n_pass, int clip, void* stream);
+int lwm_vq_conv_cin3(const float* x, const float* w_hwio, const float* bias, float* y, int N, int H, int W, int Cout,
+                     void* stream);
+int lwm_vq_argmin(const float* z, const float* codebook, int* idx, float* zq_st, void* workspace, int N, int n_e,
+                  int e_dim, void* stream);
+int lwm_vq_gather(const int* idx, const float* codebook, float* out, long long N, int n_e, int e_dim, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -21,6 +21,12 @@ _SIGNATURES = {
                                                        c_float, c_void_p],
     "lwm_cast_f32_to_bf16": [c_void_p, c_void_p, c_ll, c_void_p],
     "lwm_add_f32": [c_void_p, c_void_p, c_ll, c_void_p],
+    "lwm_vq_gn_stats": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p],
+    "lwm_vq_prep": [c_void_p] * 6 + [c_int] * 7 + [c_float, c_void_p],
+    "lwm_vq_conv2d": [c_void_p] * 7 + [c_int] * 13 + [c_void_p],
+    "lwm_vq_conv_cin3": [c_void_p] * 4 + [c_int] * 4 + [c_void_p],
+    "lwm_vq_argmin": [c_void_p] * 5 + [c_int] * 3 + [c_void_p],
+    "lwm_vq_gather": [c_void_p] * 3 + [c_ll, c_int, c_int, c_void_p],
 }
 
 

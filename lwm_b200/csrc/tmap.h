@@ -27,7 +27,7 @@ inline PFN_encodeTiled get_encode_fn() {
 // dims[rank] (innermost first), strides_bytes[rank-1] (for dims 1..rank-1), box[rank].
 inline bool encode_tmap(CUtensorMap* out, CUtensorMapDataType dt, int rank, const void* base,
                         const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box,
-                        CUtensorMapSwizzle swz) {
+                        CUtensorMapSwizzle swz, const uint32_t* elem_strides = nullptr) {
   PFN_encodeTiled fn = get_encode_fn();
   if (!fn) return false;
   cuuint64_t d[5], s[4];
@@ -35,7 +35,7 @@ inline bool encode_tmap(CUtensorMap* out, CUtensorMapDataType dt, int rank, cons
   for (int i = 0; i < rank; ++i) {
     d[i] = dims[i];
     b[i] = box[i];
-    es[i] = 1;
+    es[i] = elem_strides ? elem_strides[i] : 1;
   }
   for (int i = 0; i < rank - 1; ++i) s[i] = strides_bytes[i];
   CUresult r = fn(out, dt, static_cast<cuuint32_t>(rank), const_cast<void*>(base), d, s, b, es,

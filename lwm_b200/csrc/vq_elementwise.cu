@@ -142,103 +142,102 @@ __global__ void conv_cin3_kernel(const float* __restrict__ x, const float* __res
 // Block = 128 threads, 16 rows of z; the codebook streams through in tiles of 128 codes
 // (thread = one code held in registers), rows broadcast from shared memory.
 // ------------------------------------------------------------------------------------------------
-constexpr int kVqRows = 16;
 constexpr int kVqDim = 64;
+constexpr int kVqSplits = 8;   // the codebook is scanned in 8 slices so that 4096 rows still fill the GPU
 
+// thread = one row of z (held in registers); the block's codebook slice streams through shared memory
+// in tiles of 128 codes (broadcast reads). Every thread visits codes in ascending order, so a strict
+// '<' keeps the first minimal index. Partial (distance, index) per slice go to `part_*`.
 __global__ void __launch_bounds__(128)
-vq_argmin_kernel(const float* __restrict__ z, const float* __restrict__ emb, int* __restrict__ idx,
-                 float* __restrict__ zq_st, int N, int n_e) {
-  __shared__ float s_z[kVqRows][kVqDim];
-  __shared__ float s_zz[kVqRows];
-  __shared__ float s_best_d[kVqRows][4];
-  __shared__ int s_best_i[kVqRows][4];
-  const int row0 = blockIdx.x * kVqRows;
-  const int nrows = min(kVqRows, N - row0);
-  for (int i = threadIdx.x; i < kVqRows * kVqDim; i += blockDim.x) {
-    const int r = i / kVqDim, d = i % kVqDim;
-    s_z[r][d] = (r < nrows) ? z[(size_t)(row0 + r) * kVqDim + d] : 0.f;
-  }
-  __syncthreads();
-  if (threadIdx.x < kVqRows) {
-    float a = 0.f;
-    for (int d = 0; d < kVqDim; ++d) a = __fadd_rn(a, __fmul_rn(s_z[threadIdx.x][d], s_z[threadIdx.x][d]));
-    s_zz[threadIdx.x] = a;
-  }
-  __syncthreads();
-  float best_d[kVqRows];
-  int best_i[kVqRows];
+vq_argmin_partial_kernel(const float* __restrict__ z, const float* __restrict__ emb, float* __restrict__ part_d,
+                         int* __restrict__ part_i, int N, int n_e) {
+  __shared__ __align__(16) float s_e[128][kVqDim];
+  __shared__ float s_ee[128];
+  const int row = blockIdx.x * 128 + threadIdx.x;
+  const int per = (n_e + kVqSplits - 1) / kVqSplits;
+  const int c_begin = blockIdx.y * per, c_end = min(n_e, c_begin + per);
+  float zr[kVqDim];
 #pragma unroll
-  for (int r = 0; r < kVqRows; ++r) {
-    best_d[r] = INFINITY;
-    best_i[r] = 0x7fffffff;
+  for (int d4 = 0; d4 < kVqDim / 4; ++d4) {
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (row < N) v = reinterpret_cast<const float4*>(z + (size_t)row * kVqDim)[d4];
+    zr[4 * d4] = v.x; zr[4 * d4 + 1] = v.y; zr[4 * d4 + 2] = v.z; zr[4 * d4 + 3] = v.w;
   }
-  for (int c0 = 0; c0 < n_e; c0 += 128) {
-    const int code = c0 + threadIdx.x;
-    if (code < n_e) {
-      float e[kVqDim];
-      const float4* src = reinterpret_cast<const float4*>(emb + (size_t)code * kVqDim);
+  float zz = 0.f;
 #pragma unroll
-      for (int d4 = 0; d4 < kVqDim / 4; ++d4) {
-        const float4 v = src[d4];
-        e[4 * d4] = v.x; e[4 * d4 + 1] = v.y; e[4 * d4 + 2] = v.z; e[4 * d4 + 3] = v.w;
-      }
+  for (int d = 0; d < kVqDim; ++d) zz = __fadd_rn(zz, __fmul_rn(zr[d], zr[d]));
+  float best_d = INFINITY;
+  int best_i = 0x7fffffff;
+  for (int c0 = c_begin; c0 < c_end; c0 += 128) {
+    __syncthreads();
+    {
+      const int code = c0 + threadIdx.x;
       float ee = 0.f;
+      if (code < c_end) {
+        const float4* src = reinterpret_cast<const float4*>(emb + (size_t)code * kVqDim);
 #pragma unroll
-      for (int d = 0; d < kVqDim; ++d) ee = __fadd_rn(ee, __fmul_rn(e[d], e[d]));
-#pragma unroll
-      for (int r = 0; r < kVqRows; ++r) {
-        float dot = 0.f;
-#pragma unroll
-        for (int d = 0; d < kVqDim; ++d) dot = __fadd_rn(dot, __fmul_rn(s_z[r][d], e[d]));
-        const float dist = __fadd_rn(__fadd_rn(s_zz[r], ee), -__fmul_rn(2.0f, dot));
-        if (dist < best_d[r]) {   // codes are visited in ascending order: strict < keeps the first index
-          best_d[r] = dist;
-          best_i[r] = code;
+        for (int d4 = 0; d4 < kVqDim / 4; ++d4) {
+          const float4 v = src[d4];
+          *reinterpret_cast<float4*>(&s_e[threadIdx.x][4 * d4]) = v;
+          ee = __fadd_rn(ee, __fmul_rn(v.x, v.x));
+          ee = __fadd_rn(ee, __fmul_rn(v.y, v.y));
+          ee = __fadd_rn(ee, __fmul_rn(v.z, v.z));
+          ee = __fadd_rn(ee, __fmul_rn(v.w, v.w));
         }
       }
+      s_ee[threadIdx.x] = ee;
     }
-  }
-  // reduce across the 128 threads: min distance, then smallest index
-  const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+    __syncthreads();
+    const int cnt = min(128, c_end - c0);
+    for (int j = 0; j < cnt; ++j) {
+      float dot = 0.f;
 #pragma unroll
-  for (int r = 0; r < kVqRows; ++r) {
-    float d = best_d[r];
-    int i = best_i[r];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const float d2 = __shfl_xor_sync(0xffffffffu, d, o);
-      const int i2 = __shfl_xor_sync(0xffffffffu, i, o);
-      if (d2 < d || (d2 == d && i2 < i)) {
-        d = d2;
-        i = i2;
+      for (int d4 = 0; d4 < kVqDim / 4; ++d4) {
+        const float4 e4 = *reinterpret_cast<const float4*>(&s_e[j][4 * d4]);
+        dot = __fadd_rn(dot, __fmul_rn(zr[4 * d4], e4.x));
+        dot = __fadd_rn(dot, __fmul_rn(zr[4 * d4 + 1], e4.y));
+        dot = __fadd_rn(dot, __fmul_rn(zr[4 * d4 + 2], e4.z));
+        dot = __fadd_rn(dot, __fmul_rn(zr[4 * d4 + 3], e4.w));
+      }
+      const float dist = __fadd_rn(__fadd_rn(zz, s_ee[j]), -__fmul_rn(2.0f, dot));
+      if (dist < best_d) {
+        best_d = dist;
+        best_i = c0 + j;
       }
     }
-    if (lane == 0) {
-      s_best_d[r][wp] = d;
-      s_best_i[r][wp] = i;
+  }
+  if (row < N) {
+    part_d[(size_t)blockIdx.y * N + row] = best_d;
+    part_i[(size_t)blockIdx.y * N + row] = best_i;
+  }
+}
+
+// merge the slices in ascending order (strict '<' => first index), emit idx and the straight-through value
+__global__ void vq_argmin_final_kernel(const float* __restrict__ z, const float* __restrict__ emb,
+                                       const float* __restrict__ part_d, const int* __restrict__ part_i,
+                                       int* __restrict__ idx, float* __restrict__ zq_st, int N) {
+  const int row = blockIdx.x * (blockDim.x / 16) + threadIdx.x / 16;
+  const int q = threadIdx.x % 16;
+  if (row >= N) return;
+  float bd = INFINITY;
+  int bi = 0x7fffffff;
+  for (int s = 0; s < kVqSplits; ++s) {
+    const float d = part_d[(size_t)s * N + row];
+    if (d < bd) {
+      bd = d;
+      bi = part_i[(size_t)s * N + row];
     }
   }
-  __syncthreads();
-  if (threadIdx.x < nrows) {
-    const int r = threadIdx.x;
-    float d = s_best_d[r][0];
-    int i = s_best_i[r][0];
-    for (int k = 1; k < 4; ++k)
-      if (s_best_d[r][k] < d || (s_best_d[r][k] == d && s_best_i[r][k] < i)) {
-        d = s_best_d[r][k];
-        i = s_best_i[r][k];
-      }
-    idx[row0 + r] = i;
-    s_best_i[r][0] = i;
-  }
-  __syncthreads();
-  if (zq_st) {  // straight-through value z + (e[idx] - z), rounded like the reference (vqgan.py:215)
-    for (int t = threadIdx.x; t < nrows * kVqDim; t += blockDim.x) {
-      const int r = t / kVqDim, d = t % kVqDim;
-      const float zv = s_z[r][d];
-      const float ev = emb[(size_t)s_best_i[r][0] * kVqDim + d];
-      zq_st[(size_t)(row0 + r) * kVqDim + d] = __fadd_rn(zv, __fadd_rn(ev, -zv));
-    }
+  if (q == 0) idx[row] = bi;
+  if (zq_st) {  // z + (e[idx] - z), rounded like the reference (vqgan.py:215)
+    const float4 zv = reinterpret_cast<const float4*>(z + (size_t)row * kVqDim)[q];
+    const float4 ev = reinterpret_cast<const float4*>(emb + (size_t)bi * kVqDim)[q];
+    float4 o;
+    o.x = __fadd_rn(zv.x, __fadd_rn(ev.x, -zv.x));
+    o.y = __fadd_rn(zv.y, __fadd_rn(ev.y, -zv.y));
+    o.z = __fadd_rn(zv.z, __fadd_rn(ev.z, -zv.z));
+    o.w = __fadd_rn(zv.w, __fadd_rn(ev.w, -zv.w));
+    reinterpret_cast<float4*>(zq_st + (size_t)row * kVqDim)[q] = o;
   }
 }
 
@@ -305,15 +304,19 @@ extern "C" int lwm_vq_conv_cin3(const float* x, const float* w_hwio, const float
   return lwm_check_launch("conv_cin3_kernel");
 }
 
-extern "C" int lwm_vq_argmin(const float* z, const float* codebook, int* idx, float* zq_st, int N, int n_e, int e_dim,
-                             void* stream) {
+extern "C" int lwm_vq_argmin(const float* z, const float* codebook, int* idx, float* zq_st, void* workspace,
+                             int N, int n_e, int e_dim, void* stream) {
   if (!lwm_check_device()) return LWM_ERR_DEVICE;
-  if (!z || !codebook || !idx) return lwm_fail(LWM_ERR_ARG, "vq_argmin: null pointer");
+  if (!z || !codebook || !idx || !workspace) return lwm_fail(LWM_ERR_ARG, "vq_argmin: null pointer");
   if (e_dim != kVqDim) return lwm_fail(LWM_ERR_SHAPE, "vq_argmin: e_dim must be 64 (quantized_embed_dim, vqgan.py:72)");
   if (N <= 0 || n_e <= 0) return lwm_fail(LWM_ERR_SHAPE, "vq_argmin: empty input");
-  vq_argmin_kernel<<<(N + kVqRows - 1) / kVqRows, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(z, codebook, idx,
-                                                                                                   zq_st, N, n_e);
-  return lwm_check_launch("vq_argmin_kernel");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  float* part_d = reinterpret_cast<float*>(workspace);            // workspace: 8 * N * (4 + 4) bytes
+  int* part_i = reinterpret_cast<int*>(part_d + (size_t)kVqSplits * N);
+  dim3 grid((N + 127) / 128, kVqSplits);
+  vq_argmin_partial_kernel<<<grid, 128, 0, st>>>(z, codebook, part_d, part_i, N, n_e);
+  vq_argmin_final_kernel<<<(N + 15) / 16, 256, 0, st>>>(z, codebook, part_d, part_i, idx, zq_st, N);
+  return lwm_check_launch("vq_argmin kernels");
 }
 
 extern "C" int lwm_vq_gather(const int* idx, const float* codebook, float* out, long long N, int n_e, int e_dim,

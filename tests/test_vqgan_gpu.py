@@ -1,0 +1,170 @@
+"""GPU parity of the VQGAN tokenizer kernels against oracle/vqgan_ref.py (flax-semantics CPU
+restatement of lwm/vqgan.py).
+
+Tolerances: relative Frobenius error <= 1e-3 (north_star) for every float tensor in the default
+'bf16x3' precision mode (measured ~1e-5); codebook indices bit-exact at the VectorQuantizer op
+boundary (identical fp32 z in, pinned operation order) and >= 99.9 % identical end to end, with
+every mismatch confined to codes whose oracle distances tie to within float32 resolution."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import rel_fro, to_np
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-3
+
+
+@pytest.fixture(scope="module")
+def vr():
+    from oracle import vqgan_ref
+    return vqgan_ref
+
+
+def _ops(precision="bf16x3"):
+    from lwm_b200.vqgan import Ops
+    return Ops(precision)
+
+
+def _pc(p):
+    from lwm_b200.vqgan import PackedConv
+    return PackedConv(p, torch.device("cuda"))
+
+
+def _gn(p):
+    return {"scale": p["scale"].cuda(), "bias": p["bias"].cuda()}
+
+
+@pytest.mark.parametrize("C,H", [(128, 32), (256, 16), (512, 16), (768, 16)])
+def test_groupnorm_silu_prep(vr, C, H):
+    g = torch.Generator().manual_seed(C)
+    x = torch.randn(2, H, H, C, generator=g) * 1.7 + 0.3
+    p = vr._gn_p(g, C)
+    ops = _ops()
+    hi, lo = ops.prep(x.cuda(), _gn(p))
+    y = hi.float() + lo.float()
+    ref = vr.silu(vr.group_norm(x, p))
+    assert rel_fro(to_np(y), ref.numpy()) < 2e-5     # hi+lo carries 16 significant bits
+
+
+@pytest.mark.parametrize("cin,cout,k,H", [(128, 128, 3, 32), (128, 256, 3, 16), (256, 256, 3, 16), (128, 256, 1, 16),
+                                          (768, 64, 3, 16), (64, 64, 1, 16), (64, 768, 3, 16), (512, 768, 3, 16),
+                                          (128, 3, 3, 32)])
+def test_conv_same(vr, cin, cout, k, H):
+    g = torch.Generator().manual_seed(cin * 7 + cout)
+    x = torch.randn(2, H, H, cin, generator=g)
+    p = vr._conv_p(g, k, cin, cout)
+    ops = _ops()
+    y = ops.conv(ops.prep(x.cuda()), _pc(p))
+    torch.cuda.synchronize()
+    ref = vr.conv2d(x.double(), {"kernel": p["kernel"].double(), "bias": p["bias"].double()})
+    assert rel_fro(to_np(y), ref.numpy()) < 1e-4
+
+
+def test_conv_bf16_fast_mode_is_bf16_accurate(vr):
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(1, 16, 16, 128, generator=g)
+    p = vr._conv_p(g, 3, 128, 128)
+    ops = _ops("bf16")
+    y = ops.conv(ops.prep(x.cuda()), _pc(p))
+    ref = vr.conv2d(x, p, round_fn=vr.round_bf16)    # same operand rounding on the CPU
+    assert rel_fro(to_np(y), ref.numpy()) < 1e-4
+
+
+def test_conv_residual_and_clip(vr):
+    g = torch.Generator().manual_seed(4)
+    x = torch.randn(1, 16, 16, 128, generator=g)
+    r = torch.randn(1, 16, 16, 128, generator=g)
+    p = vr._conv_p(g, 3, 128, 128)
+    ops = _ops()
+    y = ops.conv(ops.prep(x.cuda()), _pc(p), residual=r.cuda(), clip=True)
+    ref = torch.clamp(vr.conv2d(x, p) + r, -1, 1)
+    assert rel_fro(to_np(y), ref.numpy()) < 1e-4
+
+
+def test_downsample_upsample_cin3(vr):
+    from lwm_b200 import vqgan as V
+    g = torch.Generator().manual_seed(5)
+    ops = _ops()
+    x = torch.randn(2, 32, 32, 128, generator=g)
+    pd = {"Conv_0": vr._conv_p(g, 3, 128, 128)}
+    y = V.Downsample(ops, x.cuda(), {"Conv_0": _pc(pd["Conv_0"])})
+    assert tuple(y.shape) == (2, 16, 16, 128)
+    assert rel_fro(to_np(y), vr.downsample(x, pd).numpy()) < 1e-4
+    xu = torch.randn(2, 16, 16, 256, generator=g)
+    pu = {"Conv_0": vr._conv_p(g, 3, 256, 256)}
+    yu = V.Upsample(ops, xu.cuda(), {"Conv_0": _pc(pu["Conv_0"])})
+    assert tuple(yu.shape) == (2, 32, 32, 256)
+    assert rel_fro(to_np(yu), vr.upsample(xu, pu).numpy()) < 1e-4
+    xi = torch.rand(2, 32, 32, 3, generator=g) * 2 - 1
+    pi = vr._conv_p(g, 3, 3, 128)
+    yi = ops.conv_cin3(xi.cuda(), _pc(pi))
+    assert rel_fro(to_np(yi), vr.conv2d(xi, pi).numpy()) < 1e-5
+
+
+def test_resnet_block(vr):
+    from lwm_b200 import vqgan as V
+    g = torch.Generator().manual_seed(6)
+    x = torch.randn(2, 16, 16, 128, generator=g)
+    p = vr._resnet_p(g, 128, 256)
+    packed = V._pack_tree(p, torch.device("cuda"))
+    y = V.ResnetBlock(_ops(), x.cuda(), packed)
+    assert rel_fro(to_np(y), vr.resnet_block(x, p).numpy()) < TOL
+
+
+@pytest.mark.parametrize("codebook", ["normal", "uniform"])
+def test_vq_argmin_bit_exact(vr, codebook):
+    g = torch.Generator().manual_seed(7)
+    n_e = 8192
+    emb = torch.randn(n_e, 64, generator=g) if codebook == "normal" else (torch.rand(n_e, 64, generator=g) * 2 - 1) / n_e
+    z = torch.randn(1000, 64, generator=g) * (1.0 if codebook == "normal" else 1e-4)
+    emb[17] = emb[4242]            # exact duplicate rows: the first index must win
+    z[5] = emb[4242]
+    ops = _ops()
+    zq, idx = ops.vq_argmin(z.cuda(), emb.cuda())
+    ref_zq, ref_idx = vr.vector_quantize(z.numpy(), emb.numpy())
+    assert np.array_equal(to_np(idx).astype(np.int32), ref_idx)
+    assert idx[5].item() == 17
+    assert np.array_equal(zq.cpu().numpy(), ref_zq)            # straight-through value, bit for bit
+    back = ops.vq_gather(idx, emb.cuda())
+    assert np.array_equal(back.cpu().numpy(), emb.numpy()[ref_idx])
+
+
+def test_encode_end_to_end(vr):
+    from lwm_b200.vqgan import VQGAN
+    params = vr.init_params(seed=0, codebook="normal")
+    g = torch.Generator().manual_seed(11)
+    x = torch.rand(1, 2, 256, 256, 3, generator=g) * 2 - 1      # [B,T,H,W,C] video input
+    tok = VQGAN(params)
+    zq, idx = tok.encode(x)
+    torch.cuda.synchronize()
+    assert tuple(zq.shape) == (1, 2, 16, 16, 64) and tuple(idx.shape) == (1, 2, 16, 16)
+    ref_zq, ref_idx, ref_h = vr.encode(x, params)
+    # pre-quantisation latent: the float parity statement
+    h = tok.model.ops.conv(tok.model.ops.prep(tok.model.encoder(x.reshape(2, 256, 256, 3).cuda())),
+                           tok.model.p["quant_conv"])
+    assert rel_fro(to_np(h), ref_h) < TOL
+    got = to_np(idx).astype(np.int32)
+    agree = (got == ref_idx).mean()
+    assert agree >= 0.999, agree
+    # any disagreement must be a float32-resolution near-tie in the oracle's own distances
+    bad = np.argwhere(got != ref_idx)
+    emb = params["quantize"]["embeddings"].numpy()
+    for b in bad:
+        zrow = ref_h.reshape(-1, 64)[np.ravel_multi_index(tuple(b[1:]), (2, 16, 16))][None]
+        d = vr.vq_distances_f32(zrow, emb)[0]
+        assert abs(d[got[tuple(b)]] - d[ref_idx[tuple(b)]]) <= 1e-4 * max(1.0, abs(d.min()))
+
+
+def test_decode_end_to_end(vr):
+    from lwm_b200.vqgan import VQGAN
+    params = vr.init_params(seed=1, codebook="normal")
+    g = torch.Generator().manual_seed(12)
+    codes = torch.randint(0, 8192, (1, 16, 16), generator=g)
+    tok = VQGAN(params)
+    y = tok.decode(codes)
+    torch.cuda.synchronize()
+    ref = vr.decode(codes.numpy(), params)
+    assert tuple(y.shape) == (1, 256, 256, 3)
+    assert float(y.abs().max()) <= 1.0
+    assert rel_fro(to_np(y), ref) < TOL
