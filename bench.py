@@ -154,6 +154,41 @@ def run_reference_arm(args, rank):
     print(json.dumps(line))
 
 
+def bench_vqgan(dev, peaks, world):
+    """VQGAN encode of a 16-frame 256x256 clip (BASELINE 'VQGAN frames/s'), synthetic weights and pixels.
+    Byte accounting = SURVEY.md §8d minimum-traffic model with fp32 activations: 815.5 MB / frame."""
+    import torch
+    from lwm_b200.vqgan import VQGAN
+    from oracle import vqgan_ref   # only to draw random parameters with the reference's shapes
+    params = vqgan_ref.init_params(seed=0, codebook="normal")
+    g = torch.Generator().manual_seed(1234)
+    x = (torch.rand(16, 256, 256, 3, generator=g) * 2 - 1).to(dev)
+    out = {}
+    for mode in ("bf16x3", "bf16"):
+        tok = VQGAN(params, precision=mode, device=str(dev))
+        for _ in range(3):
+            tok.encode(x)
+        torch.cuda.synchronize()
+        a, b2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        n = 5
+        for _ in range(n):
+            tok.encode(x)
+        b2.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b2) / n
+        flops = 16 * 216.6e9
+        out[mode] = {"ms_per_16_frames": ms, "frames_per_s_per_gpu": 16 / (ms * 1e-3),
+                     "frames_per_s_all_gpus": world * 16 / (ms * 1e-3),
+                     "hbm_roofline_frac_fp32_accounting": (16 * 815.5e6 / (ms * 1e-3) / 1e9) / peaks["hbm"],
+                     "tensor_tflops_algorithmic": flops / (ms * 1e-3) / 1e12,
+                     "tensor_frac_of_bf16_peak": flops * (3 if mode == "bf16x3" else 1) / (ms * 1e-3) / 1e12 / peaks["sustained"]}
+        del tok
+    out["note"] = ("bf16x3 = split-bf16 operands (3 MMAs), the mode that meets the 1e-3 parity bound vs the fp32 "
+                   "reference; bf16 = single-pass fast mode (1e-2). Replicas only across GPUs (frames independent).")
+    return out
+
+
 # ------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
@@ -304,6 +339,11 @@ def main():
     bytes_in = 4 * hq.numel() * 2
     bytes_out = 4 * hq.numel() * 2
 
+    # ---- VQGAN encode: 16 frames of 256x256 (replicas: every rank encodes its own clip, no collective)
+    vq = None
+    if not args.no_vqgan:
+        vq = bench_vqgan(dev, peaks, world)
+
     if rank == 0:
         total_flops = 3.5 * f_fwd(S)
         line = {
@@ -323,6 +363,8 @@ def main():
         }
         if roof:
             line["roofline"] = roof
+        if vq:
+            line["vqgan"] = vq
         if not args.no_cpu_baseline:
             cores = min(len(os.sched_getaffinity(0)), 32)   # more threads only add contention at this size
             torch.set_num_threads(cores)
