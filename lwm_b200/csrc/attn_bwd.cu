@@ -15,10 +15,14 @@
 //     dK  += dS^T Q     SS  dS^T from smem (K-major)  x Q MN-major
 //     dQ   = dS  K      SS  the SAME smem tile read MN-major x K MN-major -> TMEM R1 (dP^T is dead)
 //   TMEM: R0 | R1 | dK | dV = 512 columns.
-//   warps 0-3 / 4-7: key row = TMEM lane; the two warpgroups split the 128 query columns. They
-//     compute P^T, dS^T and drain dQ: TMEM -> swizzled smem -> TMA reduce-add (fp32) into dq_acc.
+//   warps 0-3 / 4-7 (compute): key row = TMEM lane; the two warpgroups split the 128 query columns and
+//     produce P^T (exp phase) and dS^T. The exp phase of Q tile i+1 is run right after dS^T(i), i.e.
+//     while the tensor pipe executes dK(i), dQ(i).
 //   warp 8: TMA loads (K,V once; Q + lse + delta double-buffered; dO single-buffered);
 //   warp 9: one lane issues the UMMAs.
+//   warps 12-15 (drain): dQ tile TMEM -> registers -> 128B-swizzled smem -> TMA reduce-add (fp32) into
+//     dq_acc, off the compute warps' critical path; it frees R1 for the next dP^T as soon as its
+//     tcgen05.ld's have landed.
 // The softmax scale is folded into dS before it is rounded to bf16, so dK and dQ need no epilogue
 // scaling. dk_acc / dv_acc are accumulated read-modify-write by the one CTA that owns the tile.
 #include "attn_common.cuh"
@@ -36,11 +40,12 @@ struct BwdParams {
   const float* delta;  // [B,H,Sq]
   float* dk_acc;       // [B,Sk,H,D] fp32
   float* dv_acc;       // [B,Sk,H,D] fp32
+  unsigned long long* prof;  // debug wait-time buffer or null
 };
 
-constexpr int kBwdThreads = 384;
+constexpr int kBwdThreads = 512;
 constexpr int kTB = kTile * kHeadDim * 2;  // 32 KB bf16 tile
-// smem map (bytes): K | V | Q0 | Q1 | dO | dS (2 x 16K halves) | stage (2 x 16K)
+// smem map (bytes): K | V | Q0 | Q1 | dO | dS | dQ staging (2 x 16K, drain warpgroup only)
 constexpr int kOffK = 0, kOffV = kTB, kOffQ = 2 * kTB, kOffDO = 4 * kTB, kOffDS = 5 * kTB, kOffStage = 6 * kTB;
 constexpr int kOffLse = 7 * kTB, kOffDelta = kOffLse + 2 * kTile * 4, kOffBars = kOffDelta + 2 * kTile * 4;
 constexpr int kBwdSmemBytes = kOffBars + 256;  // 231,680 B of the 232,448 B a CTA may own
@@ -101,7 +106,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     mbar_init(&bars.p_ready, 256);
     mbar_init(&bars.ds_ready, 256);
     mbar_init(&bars.dq_full, 1);
-    mbar_init(&bars.dq_drained, 256);
+    mbar_init(&bars.dq_drained, 128);
     mbar_init(&bars.final_bar, 1);
     fence_mbar_init();
     tma_prefetch_desc(&tmQ);
@@ -116,8 +121,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const uint32_t tmem = tmem_base_s;
   constexpr uint32_t R0 = 0, R1 = 128, RDK = 256, RDV = 384;
 
-  if (warp >= 8) {
-    setmaxnreg_dec<56>();
+  if (warp >= 8 && warp < 12) {
+    setmaxnreg_dec<40>();
     if (warp == 8) {
       // ---------------------------------------------------------------- TMA producer
       if (lane == 0) {
@@ -140,66 +145,140 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
     } else if (warp == 9) {
       // ---------------------------------------------------------------- UMMA issuer
-      if (lane == 0) {
+      // Whole warp in uniform control flow (descriptors in uniform registers); the elected lane issues.
+      {
+        const bool leader = elect_one();
         constexpr uint32_t id_kk = make_idesc_bf16(kTile, kTile, false, false);     // S^T, dP^T
         constexpr uint32_t id_kn = make_idesc_bf16(kTile, kHeadDim, false, true);   // dV (A tmem), dK
         constexpr uint32_t id_nn = make_idesc_bf16(kTile, kHeadDim, true, true);    // dQ
         const uint32_t aK = smem_u32(smem + kOffK), aV = smem_u32(smem + kOffV), aDO = smem_u32(smem + kOffDO),
-                       aDS = smem_u32(smem + kOffDS);
+                       aDS = smem_u32(smem + kOffDS), aQ0 = smem_u32(smem + kOffQ);
+        // base descriptors, built once; per-k-step variants are one add away
+        const uint64_t dK_k = desc_kmajor_sw128(aK), dK_n = desc_mnmajor_sw128(aK, kTB / 2);
+        const uint64_t dV_k = desc_kmajor_sw128(aV);
+        const uint64_t dDO_k = desc_kmajor_sw128(aDO), dDO_n = desc_mnmajor_sw128(aDO, kTB / 2);
+        const uint64_t dDS_k = desc_kmajor_sw128(aDS), dDS_n = desc_mnmajor_sw128(aDS, kTB / 2);
+        const uint64_t dQ_k[2] = {desc_kmajor_sw128(aQ0), desc_kmajor_sw128(aQ0 + kTB)};
+        const uint64_t dQ_n[2] = {desc_mnmajor_sw128(aQ0, kTB / 2), desc_mnmajor_sw128(aQ0 + kTB, kTB / 2)};
         auto koff = [](int ks) { return uint32_t((ks >> 2) * (kTB / 2) + (ks & 3) * 32); };
         auto issue_st = [&](int it) {
-          const uint32_t aQ = smem_u32(smem + kOffQ + (it & 1) * kTB);
+          if (leader) {
 #pragma unroll
-          for (int ks = 0; ks < 8; ++ks)
-            umma_ss(tmem + R0, desc_kmajor_sw128(aK + koff(ks)), desc_kmajor_sw128(aQ + koff(ks)), id_kk, ks > 0);
-          umma_commit(&bars.s_full);
+            for (int ks = 0; ks < 8; ++ks)
+              umma_ss(tmem + R0, desc_advance(dK_k, koff(ks)), desc_advance(dQ_k[it & 1], koff(ks)), id_kk, ks > 0);
+            umma_commit(&bars.s_full);
+          }
         };
+        // prof slots 0..5: do_full, dq_drained, p_ready, q_full(next), ds_ready, (unused); 6: total
+        WaitProf wp;
+        wp.init(lane == 0 ? p.prof : nullptr);
         mbar_wait(&bars.kv_full, 0);
         mbar_wait(&bars.q_full[0], 0);
         tc_fence_after();
+        const long long t_start = clock64();
         issue_st(0);
         for (int it = 0; it < nq; ++it) {
-          const uint32_t aQ = smem_u32(smem + kOffQ + (it & 1) * kTB);
-          mbar_wait(&bars.do_full, it & 1);
-          if (it > 0) mbar_wait(&bars.dq_drained, (it - 1) & 1);
+          wp.wait(&bars.do_full, it & 1, 0);
+          if (it > 0) wp.wait(&bars.dq_drained, (it - 1) & 1, 1);
           tc_fence_after();
+          if (leader) {
 #pragma unroll
-          for (int ks = 0; ks < 8; ++ks)  // dP^T = V dO^T
-            umma_ss(tmem + R1, desc_kmajor_sw128(aV + koff(ks)), desc_kmajor_sw128(aDO + koff(ks)), id_kk, ks > 0);
-          umma_commit(&bars.dp_full);
-          mbar_wait(&bars.p_ready, it & 1);
+            for (int ks = 0; ks < 8; ++ks)  // dP^T = V dO^T
+              umma_ss(tmem + R1, desc_advance(dV_k, koff(ks)), desc_advance(dDO_k, koff(ks)), id_kk, ks > 0);
+            umma_commit(&bars.dp_full);
+          }
+          wp.wait(&bars.p_ready, it & 1, 2);
           tc_fence_after();
+          if (leader) {
 #pragma unroll
-          for (int ks = 0; ks < 8; ++ks)  // dV += P^T dO ; P^T halves live at R0+[0,32) and R0+[64,96)
-            umma_ts(tmem + RDV, tmem + R0 + (ks >> 2) * 64 + (ks & 3) * 8,
-                    desc_mnmajor_sw128(aDO + ks * 2048, kTB / 2), id_kn, (it > 0) || ks > 0);
-          umma_commit(&bars.do_empty);
+            for (int ks = 0; ks < 8; ++ks)  // dV += P^T dO ; P^T halves live at R0+[0,32) and R0+[64,96)
+              umma_ts(tmem + RDV, tmem + R0 + (ks >> 2) * 64 + (ks & 3) * 8, desc_advance(dDO_n, ks * 2048), id_kn,
+                      (it > 0) || ks > 0);
+            umma_commit(&bars.do_empty);
+          }
           if (it + 1 < nq) {
-            mbar_wait(&bars.q_full[(it + 1) & 1], ((it + 1) >> 1) & 1);
+            wp.wait(&bars.q_full[(it + 1) & 1], ((it + 1) >> 1) & 1, 3);
             tc_fence_after();
             issue_st(it + 1);
           }
-          mbar_wait(&bars.ds_ready, it & 1);
+          wp.wait(&bars.ds_ready, it & 1, 4);
           tc_fence_after();
+          if (leader) {
 #pragma unroll
-          for (int ks = 0; ks < 8; ++ks)  // dK += dS^T Q
-            umma_ss(tmem + RDK, desc_kmajor_sw128(aDS + koff(ks)), desc_mnmajor_sw128(aQ + ks * 2048, kTB / 2),
-                    id_kn, (it > 0) || ks > 0);
+            for (int ks = 0; ks < 8; ++ks)  // dQ = dS K  (first: its drain then overlaps the dK UMMAs)
+              umma_ss(tmem + R1, desc_advance(dDS_n, ks * 2048), desc_advance(dK_n, ks * 2048), id_nn, ks > 0);
+            umma_commit(&bars.dq_full);
 #pragma unroll
-          for (int ks = 0; ks < 8; ++ks)  // dQ = dS K
-            umma_ss(tmem + R1, desc_mnmajor_sw128(aDS + ks * 2048, kTB / 2),
-                    desc_mnmajor_sw128(aK + ks * 2048, kTB / 2), id_nn, ks > 0);
-          umma_commit(&bars.dq_full);
-          umma_commit(&bars.q_empty[it & 1]);
+            for (int ks = 0; ks < 8; ++ks)  // dK += dS^T Q
+              umma_ss(tmem + RDK, desc_advance(dDS_k, koff(ks)), desc_advance(dQ_n[it & 1], ks * 2048), id_kn,
+                      (it > 0) || ks > 0);
+            umma_commit(&bars.q_empty[it & 1]);
+          }
         }
-        umma_commit(&bars.final_bar);
+        if (leader) umma_commit(&bars.final_bar);
+        wp.flush(0, 6, clock64() - t_start);
       }
     }
+  } else if (warp >= 12) {
+    // ------------------------------------------------------------------ dQ drain warpgroup
+    setmaxnreg_dec<88>();
+    const int r = threadIdx.x & (kTile - 1);   // TMEM lane = query row of the dQ tile
+    const uint32_t tR1 = tmem + (uint32_t((warp & 3) * 32) << 16) + R1;
+    uint8_t* stage = smem + kOffStage;
+    const bool is_issuer = (threadIdx.x & 127) == 0;
+    WaitProf wp;
+    wp.init(is_issuer ? p.prof : nullptr);
+    const long long t_start = clock64();
+    for (int it = 0; it < nq; ++it) {
+      const int q_tile_row0 = (i_start + it) * kTile;
+      wp.wait(&bars.dq_full, it & 1, 0);
+      tc_fence_after();
+      // previous iteration's TMA reduces have long finished reading the staging buffers
+      if (is_issuer) tma_wait_group_read<0>();
+      named_bar_sync(3, 128);
+      auto stage_out = [&](const uint32_t (&a0)[32], const uint32_t (&a1)[32]) {
+#pragma unroll
+        for (int c16 = 0; c16 < 8; ++c16) {
+          *reinterpret_cast<uint4*>(stage + swz128_offset(r, c16)) =
+              make_uint4(a0[4 * c16], a0[4 * c16 + 1], a0[4 * c16 + 2], a0[4 * c16 + 3]);
+          *reinterpret_cast<uint4*>(stage + kTB / 2 + swz128_offset(r, c16)) =
+              make_uint4(a1[4 * c16], a1[4 * c16 + 1], a1[4 * c16 + 2], a1[4 * c16 + 3]);
+        }
+      };
+      auto reduce_out = [&](int half) {
+        fence_proxy_async_smem();
+        named_bar_sync(3, 128);
+        if (is_issuer) {
+          tma_reduce_add_4d(&tmDQ, stage, half * 64, h, q_tile_row0, b);
+          tma_reduce_add_4d(&tmDQ, stage + kTB / 2, half * 64 + 32, h, q_tile_row0, b);
+          tma_commit_group();
+        }
+      };
+      {
+        uint32_t a0[32], a1[32];
+        tmem_ld_x32(tR1, a0);
+        tmem_ld_x32(tR1 + 32, a1);
+        tmem_wait_ld();
+        stage_out(a0, a1);
+        tmem_ld_x32(tR1 + 64, a0);
+        tmem_ld_x32(tR1 + 96, a1);
+        tmem_wait_ld();
+        tc_fence_before();
+        mbar_arrive(&bars.dq_drained);   // every lane of dQ has been read: R1 is free for the next dP^T
+        reduce_out(0);
+        if (is_issuer) tma_wait_group_read<0>();
+        named_bar_sync(3, 128);
+        stage_out(a0, a1);
+        reduce_out(1);
+      }
+    }
+    if (is_issuer) tma_wait_group<0>();
+    wp.flush(16, 1, clock64() - t_start);
   } else {
     // ------------------------------------------------------------------ compute warpgroups
-    setmaxnreg_inc<224>();
+    setmaxnreg_inc<192>();
     const int wg = warp >> 2;                  // 0: query columns [0,64) ; 1: [64,128)
-    const int r = threadIdx.x & (kTile - 1);   // TMEM lane = key row (S^T, dP^T, dK, dV) / query row (dQ)
+    const int r = threadIdx.x & (kTile - 1);   // TMEM lane = key row (S^T, dP^T, dK, dV)
     const uint32_t lane_off = uint32_t((warp & 3) * 32) << 16;
     const uint32_t tR0 = tmem + lane_off + R0 + wg * 64;
     const uint32_t tR1 = tmem + lane_off + R1 + wg * 64;
@@ -213,29 +292,31 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       bias_t = p.mask.bias[(long long)b * p.mask.bias_stride + k_pos] * kLog2e;
       key_masked = bias_t < kMaskedLogit;
     }
-    uint8_t* my_ds = smem + kOffDS + wg * (kTB / 2);        // this warpgroup's half of the dS^T tile
-    uint8_t* my_stage = smem + kOffStage + wg * (kTB / 2);  // + its dedicated staging chunk
-    const bool is_issuer = (threadIdx.x & 127) == 0;
+    uint8_t* my_ds = smem + kOffDS + wg * (kTB / 2);   // this warpgroup's 64 query columns of the dS^T tile
+    float pr[64];
+    // prof slots 8..10: q_full, s_full, dp_full ; 11: total (thread 0 only)
+    WaitProf wp;
+    wp.init(threadIdx.x == 0 ? p.prof : nullptr);
+    const long long t_start = clock64();
 
-    for (int it = 0; it < nq; ++it) {
+    // A) P^T = exp2(S^T * scale_log2 (+bias) - lse2) for Q tile `it`; bf16 P^T overwrites this
+    //    warpgroup's half of S^T in TMEM (32 packed columns).
+    auto phase_a = [&](int it) {
       const int st = it & 1;
-      const int q_tile_row0 = (i_start + it) * kTile;
-      const long long q_tile_pos = (long long)p.mask.q_pos0 + q_tile_row0;
+      const long long q_tile_pos = (long long)p.mask.q_pos0 + (long long)(i_start + it) * kTile;
       const bool need_mask = has_bias || has_seg ||
                              (p.mask.causal && (q_tile_pos < (long long)p.mask.k_pos0 + (long long)n * kTile + kTile - 1));
-      // ---- A) P^T = exp2(S^T * scale_log2 (+bias) - lse2)
-      mbar_wait(&bars.q_full[st], (it >> 1) & 1);  // lse / delta of this Q tile are in smem
-      mbar_wait(&bars.s_full, it & 1);
+      wp.wait(&bars.q_full[st], (it >> 1) & 1, 0);  // lse / delta of this Q tile are in smem
+      wp.wait(&bars.s_full, it & 1, 1);
       tc_fence_after();
-      float pr[64];
-      {
-        uint32_t s[2][32];
-        tmem_ld_x32(tR0, s[0]);
-        tmem_ld_x32(tR0 + 32, s[1]);
-        tmem_wait_ld();
-        const float4* lse4 = reinterpret_cast<const float4*>(&s_lse[st][wg * 64]);
 #pragma unroll
-        for (int c4 = 0; c4 < 16; ++c4) {
+      for (int hh = 0; hh < 2; ++hh) {
+        uint32_t s[32];
+        tmem_ld_x32(tR0 + hh * 32, s);
+        tmem_wait_ld();
+        const float4* lse4 = reinterpret_cast<const float4*>(&s_lse[st][wg * 64 + hh * 32]);
+#pragma unroll
+        for (int c4 = 0; c4 < 8; ++c4) {
           const float4 l4 = lse4[c4];
           const float ls[4] = {l4.x, l4.y, l4.z, l4.w};
 #pragma unroll
@@ -244,85 +325,66 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             // lse at the masked level (row never saw an unmasked key; padded rows in the reference):
             // fp32 cannot resolve logits against it, so such rows get p = 0, i.e. no gradient
             const float nl2 = (ls[e] < -1.0e29f) ? -INFINITY : -ls[e] * kLog2e;
-            float tv = __uint_as_float(s[c >> 5][c & 31]) * p.scale_log2;
+            float tv = __uint_as_float(s[c]) * p.scale_log2;
             if (need_mask) {
               tv = key_masked ? kMaskedLogit : tv + bias_t;
-              const long long q_pos = q_tile_pos + wg * 64 + c;
+              const long long q_pos = q_tile_pos + wg * 64 + hh * 32 + c;
               if (has_seg && seg_row[q_pos] != my_seg) tv = kMaskedLogit;
               if (p.mask.causal && q_pos < k_pos) tv = kMaskedLogit;
             }
-            pr[c] = ex2f(tv + nl2);
+            pr[hh * 32 + c] = ex2f(tv + nl2);
           }
         }
-        uint32_t pk[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) pk[i] = pack_bf16x2(pr[2 * i], pr[2 * i + 1]);
-        tmem_st_x32(tR0, pk);  // P^T half: 32 packed columns at the start of this warpgroup's S^T half
-        tmem_wait_st();
-        tc_fence_before();
-        mbar_arrive(&bars.p_ready);
       }
-      // ---- B) dS^T = P^T o (dP^T - delta) * scale  -> smem (bf16, 128B-swizzled K-major tile)
-      mbar_wait(&bars.dp_full, it & 1);
-      tc_fence_after();
-      {
-        uint32_t d[2][32];
-        tmem_ld_x32(tR1, d[0]);
-        tmem_ld_x32(tR1 + 32, d[1]);
-        tmem_wait_ld();
-        if (it > 0) {
-          // the previous drain's TMA reduce must have finished reading this warpgroup's buffers
-          if (is_issuer) tma_wait_group_read<0>();
-          named_bar_sync(1 + wg, 128);
-        }
-        const float4* dl4 = reinterpret_cast<const float4*>(&s_delta[st][wg * 64]);
+      // all 64 logits of this half have been read: the packed P^T may overwrite columns [0,32)
+      uint32_t pk[32];
 #pragma unroll
-        for (int c16 = 0; c16 < 8; ++c16) {  // 8 bf16 (16 B) per store
+      for (int i = 0; i < 32; ++i) pk[i] = pack_bf16x2(pr[2 * i], pr[2 * i + 1]);
+      tmem_st_x32(tR0, pk);
+      tmem_wait_st();
+      tc_fence_before();
+      mbar_arrive(&bars.p_ready);
+    };
+
+    // B) dS^T = P^T o (dP^T - delta) * scale  -> smem (bf16, 128B-swizzled K-major tile)
+    auto phase_b = [&](int it) {
+      const int st = it & 1;
+      wp.wait(&bars.dp_full, it & 1, 2);
+      tc_fence_after();
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        uint32_t d[32];
+        tmem_ld_x32(tR1 + hh * 32, d);
+        tmem_wait_ld();
+        const float4* dl4 = reinterpret_cast<const float4*>(&s_delta[st][wg * 64 + hh * 32]);
+#pragma unroll
+        for (int c16 = 0; c16 < 4; ++c16) {  // 8 bf16 (16 B) per store
           float dsv[8];
 #pragma unroll
-          for (int hh = 0; hh < 2; ++hh) {
-            const float4 d4 = dl4[c16 * 2 + hh];
+          for (int h2 = 0; h2 < 2; ++h2) {
+            const float4 d4 = dl4[c16 * 2 + h2];
             const float dl[4] = {d4.x, d4.y, d4.z, d4.w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              const int c = c16 * 8 + hh * 4 + e;
-              dsv[hh * 4 + e] = pr[c] * (__uint_as_float(d[c >> 5][c & 31]) - dl[e]) * p.scale;
+              const int c = c16 * 8 + h2 * 4 + e;
+              dsv[h2 * 4 + e] = pr[hh * 32 + c] * (__uint_as_float(d[c]) - dl[e]) * p.scale;
             }
           }
           const uint4 v4 = make_uint4(pack_bf16x2(dsv[0], dsv[1]), pack_bf16x2(dsv[2], dsv[3]),
                                       pack_bf16x2(dsv[4], dsv[5]), pack_bf16x2(dsv[6], dsv[7]));
-          *reinterpret_cast<uint4*>(my_ds + swz128_offset(r, c16)) = v4;
-        }
-        fence_proxy_async_smem();
-        mbar_arrive(&bars.ds_ready);
-      }
-      // ---- C) drain dQ (rows = queries) : TMEM -> smem (fp32, 32-column swizzled chunks) -> TMA reduce-add
-      mbar_wait(&bars.dq_full, it & 1);
-      tc_fence_after();
-      {
-        uint32_t a[2][32];
-        tmem_ld_x32(tR1, a[0]);
-        tmem_ld_x32(tR1 + 32, a[1]);
-        tmem_wait_ld();
-        tc_fence_before();
-        mbar_arrive(&bars.dq_drained);  // R1 may be overwritten by the next dP^T
-#pragma unroll
-        for (int ch = 0; ch < 2; ++ch) {
-          uint8_t* dst = ch == 0 ? my_stage : my_ds;  // dS^T half is dead once dq_full fired
-#pragma unroll
-          for (int c16 = 0; c16 < 8; ++c16)
-            *reinterpret_cast<uint4*>(dst + swz128_offset(r, c16)) =
-                make_uint4(a[ch][4 * c16], a[ch][4 * c16 + 1], a[ch][4 * c16 + 2], a[ch][4 * c16 + 3]);
-        }
-        fence_proxy_async_smem();
-        named_bar_sync(1 + wg, 128);
-        if (is_issuer) {
-          tma_reduce_add_4d(&tmDQ, my_stage, wg * 64, h, q_tile_row0, b);
-          tma_reduce_add_4d(&tmDQ, my_ds, wg * 64 + 32, h, q_tile_row0, b);
-          tma_commit_group();
+          *reinterpret_cast<uint4*>(my_ds + swz128_offset(r, hh * 4 + c16)) = v4;
         }
       }
+      fence_proxy_async_smem();
+      mbar_arrive(&bars.ds_ready);
+    };
+
+    phase_a(0);
+    for (int it = 0; it < nq; ++it) {
+      phase_b(it);
+      if (it + 1 < nq) phase_a(it + 1);   // overlaps the dK(it), dQ(it) UMMAs
     }
+    wp.flush(8, 3, clock64() - t_start);
     // ------------------------------------------------------------------ epilogue: dK (wg 0) / dV (wg 1)
     mbar_wait(&bars.final_bar, 0);
     tc_fence_after();
@@ -347,7 +409,6 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         }
       }
     }
-    if (is_issuer) tma_wait_group<0>();
   }
   tc_fence_before();
   __syncthreads();
@@ -397,6 +458,7 @@ extern "C" int lwm_attn_bwd_step(const void* q, const void* k, const void* v, co
   p.mask.bias = bias; p.mask.bias_stride = bias_stride;
   p.mask.seg = segment_ids; p.mask.seg_stride = seg_stride;
   p.lse = lse; p.delta = delta; p.dk_acc = dk_acc; p.dv_acc = dv_acc;
+  p.prof = lwm_prof_buffer();
   static bool attr_set = false;
   if (!attr_set) {
     if (cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmemBytes) !=

@@ -34,6 +34,7 @@ struct FwdParams {
   float* acc_m;        // [B,H,Sq]     running max, log2 domain
   float* acc_l;        // [B,H,Sq]     running denominator
   int first, last;
+  unsigned long long* prof;  // debug wait-time buffer or null
 };
 
 constexpr int kFwdStages = 4;
@@ -125,62 +126,74 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     }
   } else if (warp == 9) {
     // ------------------------------------------------------------------ UMMA issuer
-    if (lane == 0 && n_kv > 0) {
+    // The whole warp runs this code in uniform control flow (descriptor math stays in uniform
+    // registers); only the elected lane executes the tcgen05 instructions.
+    if (n_kv > 0) {
+      const bool leader = elect_one();
       constexpr uint32_t idesc_s = make_idesc_bf16(kTile, kTile, false, false);     // S = Q K^T
       constexpr uint32_t idesc_o = make_idesc_bf16(kTile, kHeadDim, false, true);   // O = P V (V MN-major)
-      const uint32_t q_addr[2] = {smem_u32(sQ), smem_u32(sQ + kFwdTileBytes)};
-      auto slot_addr = [&](int i) { return smem_u32(sKV + (i % kFwdStages) * kFwdTileBytes); };
-      auto wait_full = [&](int i) {
-        mbar_wait(&bars.kv_full[i % kFwdStages], (i / kFwdStages) & 1);
+      const uint64_t q_desc[2] = {desc_kmajor_sw128(smem_u32(sQ)), desc_kmajor_sw128(smem_u32(sQ + kFwdTileBytes))};
+      const uint32_t kv_base = smem_u32(sKV);
+      auto wait_full_p = [&](int i, WaitProf& w, int slot) {
+        w.wait(&bars.kv_full[i % kFwdStages], (i / kFwdStages) & 1, slot);
         tc_fence_after();
       };
       auto issue_s = [&](int t, int i) {  // i = ring index of K(j)
-        const uint32_t kb = slot_addr(i);
+        const uint64_t kd = desc_kmajor_sw128(kv_base + (i % kFwdStages) * kFwdTileBytes);
+        if (leader) {
 #pragma unroll
-        for (int ks = 0; ks < kHeadDim / 16; ++ks) {
-          const uint32_t off = (ks >> 2) * (kFwdTileBytes / 2) + (ks & 3) * 32;
-          umma_ss(tmem + t * kTile, desc_kmajor_sw128(q_addr[t] + off), desc_kmajor_sw128(kb + off), idesc_s,
-                  ks > 0);
+          for (int ks = 0; ks < kHeadDim / 16; ++ks) {
+            const uint32_t off = (ks >> 2) * (kFwdTileBytes / 2) + (ks & 3) * 32;
+            umma_ss(tmem + t * kTile, desc_advance(q_desc[t], off), desc_advance(kd, off), idesc_s, ks > 0);
+          }
+          umma_commit(&bars.s_full[t]);
         }
-        umma_commit(&bars.s_full[t]);
       };
       auto issue_pv = [&](int t, int i, bool accumulate) {  // i = ring index of V(j)
-        const uint32_t vb = slot_addr(i);
+        const uint64_t vd = desc_mnmajor_sw128(kv_base + (i % kFwdStages) * kFwdTileBytes, kFwdTileBytes / 2);
+        if (leader) {
 #pragma unroll
-        for (int ks = 0; ks < kTile / 16; ++ks) {
-          umma_ts(tmem + 2 * kTile + t * kHeadDim, tmem + t * kTile + ks * 8,
-                  desc_mnmajor_sw128(vb + ks * 2048, kFwdTileBytes / 2), idesc_o, accumulate || ks > 0);
+          for (int ks = 0; ks < kTile / 16; ++ks)
+            umma_ts(tmem + 2 * kTile + t * kHeadDim, tmem + t * kTile + ks * 8, desc_advance(vd, ks * 2048), idesc_o,
+                    accumulate || ks > 0);
         }
       };
+      // prof slots 32..35: kv_full(V), p_ready0, kv_full(K next), p_ready1 ; 36: total
+      WaitProf wp;
+      wp.init(lane == 0 ? p.prof : nullptr);
       mbar_wait(&bars.q_full[0], 0);
       if (valid1) mbar_wait(&bars.q_full[1], 0);
-      wait_full(0);
+      wait_full_p(0, wp, 0);
+      const long long t_start = clock64();
       issue_s(0, 0);
       if (valid1) issue_s(1, 0);
-      umma_commit(&bars.kv_empty[0]);
+      if (leader) umma_commit(&bars.kv_empty[0]);
       for (int j = 0; j < n_kv; ++j) {
         const int iv = 2 * j + 1, ikn = 2 * j + 2;
         const bool more = (j + 1) < n_kv;
-        wait_full(iv);
-        mbar_wait(&bars.p_ready[0], j & 1);
+        wait_full_p(iv, wp, 0);
+        wp.wait(&bars.p_ready[0], j & 1, 1);
         tc_fence_after();
         issue_pv(0, iv, j > 0);
         if (more) {
-          wait_full(ikn);
+          wait_full_p(ikn, wp, 2);
           issue_s(0, ikn);
-        } else {
+        } else if (leader) {
           umma_commit(&bars.o_final[0]);
         }
         if (valid1) {
-          mbar_wait(&bars.p_ready[1], j & 1);
+          wp.wait(&bars.p_ready[1], j & 1, 3);
           tc_fence_after();
           issue_pv(1, iv, j > 0);
           if (more) issue_s(1, ikn);
-          else umma_commit(&bars.o_final[1]);
+          else if (leader) umma_commit(&bars.o_final[1]);
         }
-        umma_commit(&bars.kv_empty[iv % kFwdStages]);
-        if (more) umma_commit(&bars.kv_empty[ikn % kFwdStages]);
+        if (leader) {
+          umma_commit(&bars.kv_empty[iv % kFwdStages]);
+          if (more) umma_commit(&bars.kv_empty[ikn % kFwdStages]);
+        }
       }
+      wp.flush(32, 4, clock64() - t_start);
     }
   }
   } else {
@@ -201,8 +214,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       const int my_seg = has_seg ? seg_row[q_pos] : 0;
 
       float m_run = -INFINITY, l_run = 0.f;
+      WaitProf wp;
+      wp.init(threadIdx.x == 0 ? p.prof : nullptr);
+      const long long t_start = clock64();
       for (int j = 0; j < n_kv; ++j) {
-        mbar_wait(&bars.s_full[t], j & 1);
+        wp.wait(&bars.s_full[t], j & 1, 0);
         tc_fence_after();
         uint32_t s[4][32];
 #pragma unroll
@@ -215,10 +231,18 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                                (p.mask.causal && (k_tile_pos + kTile - 1 > (long long)p.mask.q_pos0 + m0 + t * kTile));
         float mx = -INFINITY;
         if (!need_mask) {
+          // 4 independent chains of 3-input max (FMNMX3): a single 128-long chain costs ~500 cycles
+          float pm0 = -INFINITY, pm1 = -INFINITY, pm2 = -INFINITY, pm3 = -INFINITY;
 #pragma unroll
           for (int c = 0; c < 4; ++c)
 #pragma unroll
-            for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(s[c][i]));
+            for (int i = 0; i < 32; i += 8) {
+              pm0 = fmaxf(fmaxf(pm0, __uint_as_float(s[c][i + 0])), __uint_as_float(s[c][i + 1]));
+              pm1 = fmaxf(fmaxf(pm1, __uint_as_float(s[c][i + 2])), __uint_as_float(s[c][i + 3]));
+              pm2 = fmaxf(fmaxf(pm2, __uint_as_float(s[c][i + 4])), __uint_as_float(s[c][i + 5]));
+              pm3 = fmaxf(fmaxf(pm3, __uint_as_float(s[c][i + 6])), __uint_as_float(s[c][i + 7]));
+            }
+          mx = fmaxf(fmaxf(pm0, pm1), fmaxf(pm2, pm3));
           mx *= scale;
         } else {
           const long long lim = p.mask.causal ? (q_pos - k_tile_pos) : (long long)kTile;  // keys c > lim are masked
@@ -287,6 +311,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         mbar_arrive(&bars.p_ready[t]);
       }
 
+      wp.flush(40, 1, clock64() - t_start);
       // ---------------------------------------------------------------- epilogue: merge carry, write
       if (n_kv > 0) {
         mbar_wait(&bars.o_final[t], 0);
@@ -396,6 +421,7 @@ extern "C" int lwm_attn_fwd_step(const void* q, const void* k, const void* v, vo
   p.out = reinterpret_cast<__nv_bfloat16*>(out);
   p.lse = lse; p.acc_o = acc_o; p.acc_m = acc_m; p.acc_l = acc_l;
   p.first = first; p.last = last;
+  p.prof = lwm_prof_buffer();
   static bool attr_set = false;
   if (!attr_set) {
     if (cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmemBytes) !=

@@ -40,3 +40,11 @@ int lwm_check_launch(const char* what) {
 
 extern "C" const char* lwm_last_error(void) { return g_last_error; }
 extern "C" int lwm_abi_version(void) { return LWM_B200_ABI_VERSION; }
+
+static unsigned long long* g_prof = nullptr;
+unsigned long long* lwm_prof_buffer() { return g_prof; }
+// debug: device buffer of >= 64 uint64 that the attention kernels fill with barrier-wait cycle counts
+extern "C" int lwm_debug_set_prof(void* device_buffer) {
+  g_prof = reinterpret_cast<unsigned long long*>(device_buffer);
+  return LWM_OK;
+}

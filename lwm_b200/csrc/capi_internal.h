@@ -13,3 +13,5 @@ enum {
 int lwm_fail(int code, const char* msg);          // records msg, returns code
 bool lwm_check_device();                          // true iff current device is compute capability 10.x
 int lwm_check_launch(const char* what);           // cudaGetLastError -> status
+
+unsigned long long* lwm_prof_buffer();                // debug wait-time buffer (null unless set)

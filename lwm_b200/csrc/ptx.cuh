@@ -151,6 +151,15 @@ LWM_DEVICE uint64_t desc_mnmajor_sw128(uint32_t saddr, uint32_t mn_chunk_stride)
   return make_smem_desc(saddr, mn_chunk_stride, 1024);
 }
 
+// Advance a descriptor's start address by `bytes` (multiple of 16). The start-address field holds
+// addr >> 4 in bits [0,14); shared memory is < 256 KB so the add never carries out of the field.
+// One 32-bit add instead of re-encoding the descriptor: the UMMA issuer is a single thread and its
+// instruction count per MMA is what bounds the tensor pipe's issue rate.
+LWM_DEVICE uint64_t desc_advance(uint64_t d, uint32_t bytes) {
+  const uint32_t lo = static_cast<uint32_t>(d) + (bytes >> 4);
+  return (d & 0xFFFFFFFF00000000ull) | lo;
+}
+
 // Instruction descriptor for kind::f16 with bf16 inputs and fp32 accumulation.
 //   [4,6) D fmt (1=f32)  [7,10) A fmt (1=bf16)  [10,13) B fmt  [15] A MN-major  [16] B MN-major
 //   [17,23) N>>3  [24,29) M>>4

@@ -119,7 +119,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constan
     }
   } else if (warp == 5) {
     // ------------------------------------------------------------------ UMMA issuer
-    if (lane == 0) {
+    // whole warp, uniform control flow; descriptors advanced by one add per k-step; elected lane issues
+    {
+      const bool leader = elect_one();
       const uint32_t idesc = make_idesc_bf16(128, p.BN, false, false);
       int it = 0, local = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
@@ -131,20 +133,23 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constan
           const int s = it % p.stages;
           mbar_wait(&full[s], (it / p.stages) & 1);
           tc_fence_after();
-          const uint32_t a_hi = smem_u32(smem + s * stage_bytes), b_hi = a_hi + kATile;
-          const uint32_t a_lo = b_hi + b_bytes, b_lo = a_lo + kATile;
+          const uint32_t a_hi = smem_u32(smem + s * stage_bytes);
+          const uint64_t dAh = desc_kmajor_sw128(a_hi), dBh = desc_kmajor_sw128(a_hi + kATile);
+          const uint64_t dAl = desc_kmajor_sw128(a_hi + kATile + b_bytes), dBl = desc_kmajor_sw128(a_hi + 2 * kATile + b_bytes);
+          if (leader) {
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks) {
-            const uint32_t o = ks * 32;
-            umma_ss(d, desc_kmajor_sw128(a_hi + o), desc_kmajor_sw128(b_hi + o), idesc, (ki | ks) != 0);
-            if (p.n_pass == 3) {
-              umma_ss(d, desc_kmajor_sw128(a_lo + o), desc_kmajor_sw128(b_hi + o), idesc, 1);
-              umma_ss(d, desc_kmajor_sw128(a_hi + o), desc_kmajor_sw128(b_lo + o), idesc, 1);
+            for (int ks = 0; ks < 4; ++ks) {
+              const uint32_t o = ks * 32;
+              umma_ss(d, desc_advance(dAh, o), desc_advance(dBh, o), idesc, (ki | ks) != 0);
+              if (p.n_pass == 3) {
+                umma_ss(d, desc_advance(dAl, o), desc_advance(dBh, o), idesc, 1);
+                umma_ss(d, desc_advance(dAh, o), desc_advance(dBl, o), idesc, 1);
+              }
             }
+            umma_commit(&empty[s]);
           }
-          umma_commit(&empty[s]);
         }
-        umma_commit(&tmem_full[acc]);
+        if (leader) umma_commit(&tmem_full[acc]);
       }
     }
   } else {
