@@ -81,6 +81,24 @@ int lwm_attn_bwd_step(const void* q, const void* k, const void* v, const void* d
                       long long bias_stride, const int* segment_ids, long long seg_stride, float softmax_scale,
                       void* stream);
 
+/* fp16-internal precision mode (optional): the tensor cores take bf16 x bf16 or fp16 x fp16 only, so the
+ * higher-precision mode converts every operand once to an exact, power-of-two-scaled fp16 copy
+ * (lwm_attn_to_f16: x16 = x / scale, scale = 2^(e-12) with e the exponent of the tensor's |max|) and keeps the
+ * probabilities P and dS at fp16's 11 significant bits instead of bf16's 8. scale_* are DEVICE scalars written
+ * by lwm_attn_to_f16; all scale factors are undone in fp32 inside the kernels. Same semantics otherwise. */
+int lwm_attn_to_f16(const void* src_bf16, void* dst_f16, float* scale_out, void* workspace4, long long n, void* stream);
+int lwm_attn_fwd_step_f16(const void* q16, const void* k16, const void* v16, const float* scale_q, const float* scale_k,
+                          const float* scale_v, void* out, float* lse, float* acc_o, float* acc_m, float* acc_l, int B,
+                          int H, int Sq, int Sk, int D, long long q_pos0, long long k_pos0, int causal,
+                          const float* bias, long long bias_stride, const int* segment_ids, long long seg_stride,
+                          float softmax_scale, int first, int last, void* stream);
+int lwm_attn_bwd_step_f16(const void* q16, const void* k16, const void* v16, const void* dout16, const float* scale_q,
+                          const float* scale_k, const float* scale_v, const float* scale_do, const float* lse,
+                          const float* delta, float* dq_acc, float* dk_acc, float* dv_acc, int B, int H, int Sq, int Sk,
+                          int D, long long q_pos0, long long k_pos0, int causal, const float* bias,
+                          long long bias_stride, const int* segment_ids, long long seg_stride, float softmax_scale,
+                          void* stream);
+
 /* Element-wise helpers used by the ring host loop. */
 int lwm_cast_f32_to_bf16(const float* src, void* dst, long long n, void* stream);
 /* dst[i] += src[i] (fp32, n % 4 == 0): folds a dK/dV partial received from a peer into the owner's accumulator. */
@@ -117,6 +135,10 @@ int lwm_vq_conv_cin3(const float* x, const float* w_hwio, const float* bias, flo
 int lwm_vq_argmin(const float* z, const float* codebook, int* idx, float* zq_st, void* workspace, int N, int n_e,
                   int e_dim, void* stream);
 int lwm_vq_gather(const int* idx, const float* codebook, float* out, long long N, int n_e, int e_dim, void* stream);
+
+/* Debug only: device buffer (>= 64 uint64) that the attention kernels fill with per-role barrier-wait cycle
+ * counts of CTA (0,0,0) (tools/prof_waits.py); NULL disables. */
+int lwm_debug_set_prof(void* device_buffer);
 
 #ifdef __cplusplus
 }

@@ -41,6 +41,7 @@ struct BwdParams {
   float* dk_acc;       // [B,Sk,H,D] fp32
   float* dv_acc;       // [B,Sk,H,D] fp32
   unsigned long long* prof;  // debug wait-time buffer or null
+  const float *scale_q, *scale_k, *scale_v, *scale_do;   // fp16 mode: device scalars (x = x16 * scale); else null
 };
 
 constexpr int kBwdThreads = 512;
@@ -65,6 +66,11 @@ LWM_DEVICE void load_tile_nb(uint8_t* dst, const CUtensorMap* tm, uint64_t* bar,
   tma_load_4d(dst + kTB / 2, tm, bar, 64, h, row0, b);
 }
 
+// kF16: fp16 operands (exact scaled copies of the bf16 inputs), P^T and dS^T kept in fp16. dS^T is
+// boosted by 2^8 before rounding (keeps it clear of fp16 subnormals); every scale factor is undone in
+// fp32 where the results leave the tensor pipe (dQ drain, dK/dV epilogue).
+constexpr float kDsBoost = 256.0f;
+template <bool kF16>
 __global__ void __launch_bounds__(kBwdThreads, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO,
@@ -148,9 +154,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       // Whole warp in uniform control flow (descriptors in uniform registers); the elected lane issues.
       {
         const bool leader = elect_one();
-        constexpr uint32_t id_kk = make_idesc_bf16(kTile, kTile, false, false);     // S^T, dP^T
-        constexpr uint32_t id_kn = make_idesc_bf16(kTile, kHeadDim, false, true);   // dV (A tmem), dK
-        constexpr uint32_t id_nn = make_idesc_bf16(kTile, kHeadDim, true, true);    // dQ
+        constexpr uint32_t kFmt = kF16 ? kFmtF16 : kFmtBF16;
+        constexpr uint32_t id_kk = make_idesc(kTile, kTile, false, false, kFmt, kFmt);     // S^T, dP^T
+        constexpr uint32_t id_kn = make_idesc(kTile, kHeadDim, false, true, kFmt, kFmt);   // dV (A tmem), dK
+        constexpr uint32_t id_nn = make_idesc(kTile, kHeadDim, true, true, kFmt, kFmt);    // dQ
         const uint32_t aK = smem_u32(smem + kOffK), aV = smem_u32(smem + kOffV), aDO = smem_u32(smem + kOffDO),
                        aDS = smem_u32(smem + kOffDS), aQ0 = smem_u32(smem + kOffQ);
         // base descriptors, built once; per-k-step variants are one add away
@@ -226,6 +233,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const uint32_t tR1 = tmem + (uint32_t((warp & 3) * 32) << 16) + R1;
     uint8_t* stage = smem + kOffStage;
     const bool is_issuer = (threadIdx.x & 127) == 0;
+    const float dq_mul = kF16 ? (*p.scale_k) * (1.0f / kDsBoost) : 1.0f;   // dQ = (dS*boost) K16 * scale_k / boost
     WaitProf wp;
     wp.init(is_issuer ? p.prof : nullptr);
     const long long t_start = clock64();
@@ -239,10 +247,16 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       auto stage_out = [&](const uint32_t (&a0)[32], const uint32_t (&a1)[32]) {
 #pragma unroll
         for (int c16 = 0; c16 < 8; ++c16) {
-          *reinterpret_cast<uint4*>(stage + swz128_offset(r, c16)) =
-              make_uint4(a0[4 * c16], a0[4 * c16 + 1], a0[4 * c16 + 2], a0[4 * c16 + 3]);
-          *reinterpret_cast<uint4*>(stage + kTB / 2 + swz128_offset(r, c16)) =
-              make_uint4(a1[4 * c16], a1[4 * c16 + 1], a1[4 * c16 + 2], a1[4 * c16 + 3]);
+          uint4 v0 = make_uint4(a0[4 * c16], a0[4 * c16 + 1], a0[4 * c16 + 2], a0[4 * c16 + 3]);
+          uint4 v1 = make_uint4(a1[4 * c16], a1[4 * c16 + 1], a1[4 * c16 + 2], a1[4 * c16 + 3]);
+          if (kF16) {
+            v0.x = __float_as_uint(__uint_as_float(v0.x) * dq_mul); v0.y = __float_as_uint(__uint_as_float(v0.y) * dq_mul);
+            v0.z = __float_as_uint(__uint_as_float(v0.z) * dq_mul); v0.w = __float_as_uint(__uint_as_float(v0.w) * dq_mul);
+            v1.x = __float_as_uint(__uint_as_float(v1.x) * dq_mul); v1.y = __float_as_uint(__uint_as_float(v1.y) * dq_mul);
+            v1.z = __float_as_uint(__uint_as_float(v1.z) * dq_mul); v1.w = __float_as_uint(__uint_as_float(v1.w) * dq_mul);
+          }
+          *reinterpret_cast<uint4*>(stage + swz128_offset(r, c16)) = v0;
+          *reinterpret_cast<uint4*>(stage + kTB / 2 + swz128_offset(r, c16)) = v1;
         }
       };
       auto reduce_out = [&](int half) {
@@ -293,6 +307,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       key_masked = bias_t < kMaskedLogit;
     }
     uint8_t* my_ds = smem + kOffDS + wg * (kTB / 2);   // this warpgroup's 64 query columns of the dS^T tile
+    // fp16 mode: logits scale picks up scale_q*scale_k; dP = dO V^T picks up scale_do*scale_v
+    const float scale_log2 = p.scale_log2 * (kF16 ? (*p.scale_q) * (*p.scale_k) : 1.0f);
+    const float dp_mul = kF16 ? (*p.scale_do) * (*p.scale_v) : 1.0f;
+    const float ds_mul = p.scale * (kF16 ? kDsBoost : 1.0f);
     float pr[64];
     // prof slots 8..10: q_full, s_full, dp_full ; 11: total (thread 0 only)
     WaitProf wp;
@@ -325,7 +343,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             // lse at the masked level (row never saw an unmasked key; padded rows in the reference):
             // fp32 cannot resolve logits against it, so such rows get p = 0, i.e. no gradient
             const float nl2 = (ls[e] < -1.0e29f) ? -INFINITY : -ls[e] * kLog2e;
-            float tv = __uint_as_float(s[c]) * p.scale_log2;
+            float tv = __uint_as_float(s[c]) * scale_log2;
             if (need_mask) {
               tv = key_masked ? kMaskedLogit : tv + bias_t;
               const long long q_pos = q_tile_pos + wg * 64 + hh * 32 + c;
@@ -339,7 +357,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       // all 64 logits of this half have been read: the packed P^T may overwrite columns [0,32)
       uint32_t pk[32];
 #pragma unroll
-      for (int i = 0; i < 32; ++i) pk[i] = pack_bf16x2(pr[2 * i], pr[2 * i + 1]);
+      for (int i = 0; i < 32; ++i) pk[i] = kF16 ? pack_f16x2(pr[2 * i], pr[2 * i + 1]) : pack_bf16x2(pr[2 * i], pr[2 * i + 1]);
       tmem_st_x32(tR0, pk);
       tmem_wait_st();
       tc_fence_before();
@@ -367,11 +385,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               const int c = c16 * 8 + h2 * 4 + e;
-              dsv[h2 * 4 + e] = pr[hh * 32 + c] * (__uint_as_float(d[c]) - dl[e]) * p.scale;
+              dsv[h2 * 4 + e] = pr[hh * 32 + c] * (__uint_as_float(d[c]) * dp_mul - dl[e]) * ds_mul;
             }
           }
-          const uint4 v4 = make_uint4(pack_bf16x2(dsv[0], dsv[1]), pack_bf16x2(dsv[2], dsv[3]),
-                                      pack_bf16x2(dsv[4], dsv[5]), pack_bf16x2(dsv[6], dsv[7]));
+          const uint4 v4 = kF16 ? make_uint4(pack_f16x2(dsv[0], dsv[1]), pack_f16x2(dsv[2], dsv[3]),
+                                             pack_f16x2(dsv[4], dsv[5]), pack_f16x2(dsv[6], dsv[7]))
+                                : make_uint4(pack_bf16x2(dsv[0], dsv[1]), pack_bf16x2(dsv[2], dsv[3]),
+                                             pack_bf16x2(dsv[4], dsv[5]), pack_bf16x2(dsv[6], dsv[7]));
           *reinterpret_cast<uint4*>(my_ds + swz128_offset(r, hh * 4 + c16)) = v4;
         }
       }
@@ -389,6 +409,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     mbar_wait(&bars.final_bar, 0);
     tc_fence_after();
     {
+      // dK = (dS*boost)^T Q16 * scale_q / boost ; dV = P^T dO16 * scale_do
+      const float acc_mul = kF16 ? (wg == 0 ? (*p.scale_q) * (1.0f / kDsBoost) : (*p.scale_do)) : 1.0f;
       const uint32_t tAcc = tmem + lane_off + (wg == 0 ? RDK : RDV);
       float* acc = (wg == 0 ? p.dk_acc : p.dv_acc) +
                    ((((long long)b * p.Sk + (long long)n * kTile + r) * p.H + h) * kHeadDim);
@@ -401,10 +423,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           float4 cur = dst[i];
-          cur.x += __uint_as_float(o[4 * i]);
-          cur.y += __uint_as_float(o[4 * i + 1]);
-          cur.z += __uint_as_float(o[4 * i + 2]);
-          cur.w += __uint_as_float(o[4 * i + 3]);
+          cur.x = fmaf(__uint_as_float(o[4 * i]), acc_mul, cur.x);
+          cur.y = fmaf(__uint_as_float(o[4 * i + 1]), acc_mul, cur.y);
+          cur.z = fmaf(__uint_as_float(o[4 * i + 2]), acc_mul, cur.z);
+          cur.w = fmaf(__uint_as_float(o[4 * i + 3]), acc_mul, cur.w);
           dst[i] = cur;
         }
       }
@@ -433,11 +455,12 @@ static bool make_f32_tmap(CUtensorMap* tm, const void* ptr, int B, int S, int H)
 
 using namespace lwm;
 
-extern "C" int lwm_attn_bwd_step(const void* q, const void* k, const void* v, const void* dout, const float* lse,
-                                 const float* delta, float* dq_acc, float* dk_acc, float* dv_acc, int B, int H,
-                                 int Sq, int Sk, int D, long long q_pos0, long long k_pos0, int causal,
-                                 const float* bias, long long bias_stride, const int* segment_ids,
-                                 long long seg_stride, float softmax_scale, void* stream) {
+static int attn_bwd_launch(const void* q, const void* k, const void* v, const void* dout, const float* lse,
+                           const float* delta, float* dq_acc, float* dk_acc, float* dv_acc, int B, int H, int Sq,
+                           int Sk, int D, long long q_pos0, long long k_pos0, int causal, const float* bias,
+                           long long bias_stride, const int* segment_ids, long long seg_stride, float softmax_scale,
+                           const float* scale_q, const float* scale_k, const float* scale_v, const float* scale_do,
+                           void* stream) {
   if (!lwm_check_device()) return LWM_ERR_DEVICE;
   if (D != kHeadDim) return lwm_fail(LWM_ERR_SHAPE, "attn_bwd: head_dim must be 128");
   if (B <= 0 || H <= 0 || Sq <= 0 || Sk <= 0 || Sq % kTile || Sk % kTile)
@@ -459,15 +482,42 @@ extern "C" int lwm_attn_bwd_step(const void* q, const void* k, const void* v, co
   p.mask.seg = segment_ids; p.mask.seg_stride = seg_stride;
   p.lse = lse; p.delta = delta; p.dk_acc = dk_acc; p.dv_acc = dv_acc;
   p.prof = lwm_prof_buffer();
+  p.scale_q = scale_q; p.scale_k = scale_k; p.scale_v = scale_v; p.scale_do = scale_do;
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmemBytes) !=
-        cudaSuccess)
+    if (cudaFuncSetAttribute(attn_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmemBytes) !=
+            cudaSuccess ||
+        cudaFuncSetAttribute(attn_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmemBytes) !=
+            cudaSuccess)
       return lwm_fail(LWM_ERR_CUDA, "attn_bwd: cannot raise dynamic shared memory limit");
     attr_set = true;
   }
   dim3 grid(Sk / kTile, H, B);
-  attn_bwd_kernel<<<grid, kBwdThreads, kBwdSmemBytes, reinterpret_cast<cudaStream_t>(stream)>>>(tq, tk, tv, tdo,
-                                                                                                tdq, p);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (scale_q) attn_bwd_kernel<true><<<grid, kBwdThreads, kBwdSmemBytes, st>>>(tq, tk, tv, tdo, tdq, p);
+  else attn_bwd_kernel<false><<<grid, kBwdThreads, kBwdSmemBytes, st>>>(tq, tk, tv, tdo, tdq, p);
   return lwm_check_launch("attn_bwd_kernel");
+}
+
+extern "C" int lwm_attn_bwd_step(const void* q, const void* k, const void* v, const void* dout, const float* lse,
+                                 const float* delta, float* dq_acc, float* dk_acc, float* dv_acc, int B, int H,
+                                 int Sq, int Sk, int D, long long q_pos0, long long k_pos0, int causal,
+                                 const float* bias, long long bias_stride, const int* segment_ids,
+                                 long long seg_stride, float softmax_scale, void* stream) {
+  return attn_bwd_launch(q, k, v, dout, lse, delta, dq_acc, dk_acc, dv_acc, B, H, Sq, Sk, D, q_pos0, k_pos0, causal,
+                         bias, bias_stride, segment_ids, seg_stride, softmax_scale, nullptr, nullptr, nullptr, nullptr, stream);
+}
+
+// fp16-operand variant: scale_* = device scalars of the four fp16 operand copies (lwm_attn_to_f16).
+extern "C" int lwm_attn_bwd_step_f16(const void* q16, const void* k16, const void* v16, const void* dout16,
+                                     const float* scale_q, const float* scale_k, const float* scale_v,
+                                     const float* scale_do, const float* lse, const float* delta, float* dq_acc,
+                                     float* dk_acc, float* dv_acc, int B, int H, int Sq, int Sk, int D,
+                                     long long q_pos0, long long k_pos0, int causal, const float* bias,
+                                     long long bias_stride, const int* segment_ids, long long seg_stride,
+                                     float softmax_scale, void* stream) {
+  if (!scale_q || !scale_k || !scale_v || !scale_do) return lwm_fail(LWM_ERR_ARG, "attn_bwd_f16: scales required");
+  return attn_bwd_launch(q16, k16, v16, dout16, lse, delta, dq_acc, dk_acc, dv_acc, B, H, Sq, Sk, D, q_pos0, k_pos0,
+                         causal, bias, bias_stride, segment_ids, seg_stride, softmax_scale, scale_q, scale_k, scale_v,
+                         scale_do, stream);
 }

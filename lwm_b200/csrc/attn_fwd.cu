@@ -35,6 +35,7 @@ struct FwdParams {
   float* acc_l;        // [B,H,Sq]     running denominator
   int first, last;
   unsigned long long* prof;  // debug wait-time buffer or null
+  const float *scale_q, *scale_k, *scale_v;   // fp16 mode: device scalars, x = x16 * scale; null => bf16 operands
 };
 
 constexpr int kFwdStages = 4;
@@ -57,6 +58,9 @@ LWM_DEVICE void load_tile(uint8_t* dst, const CUtensorMap* tm, uint64_t* bar, in
   tma_load_4d(dst + kFwdTileBytes / 2, tm, bar, 64, h, row0, b);
 }
 
+// kF16: operands are IEEE fp16 (exact, scaled copies of the bf16 inputs) and P is kept in fp16
+// (11 significant bits instead of 8) — the precision mode that meets 1e-3 on white-noise inputs.
+template <bool kF16>
 __global__ void __launch_bounds__(kFwdThreads, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const FwdParams p) {
@@ -130,8 +134,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     // registers); only the elected lane executes the tcgen05 instructions.
     if (n_kv > 0) {
       const bool leader = elect_one();
-      constexpr uint32_t idesc_s = make_idesc_bf16(kTile, kTile, false, false);     // S = Q K^T
-      constexpr uint32_t idesc_o = make_idesc_bf16(kTile, kHeadDim, false, true);   // O = P V (V MN-major)
+      constexpr uint32_t kFmt = kF16 ? kFmtF16 : kFmtBF16;
+      constexpr uint32_t idesc_s = make_idesc(kTile, kTile, false, false, kFmt, kFmt);     // S = Q K^T
+      constexpr uint32_t idesc_o = make_idesc(kTile, kHeadDim, false, true, kFmt, kFmt);   // O = P V (V MN-major)
       const uint64_t q_desc[2] = {desc_kmajor_sw128(smem_u32(sQ)), desc_kmajor_sw128(smem_u32(sQ + kFwdTileBytes))};
       const uint32_t kv_base = smem_u32(sKV);
       auto wait_full_p = [&](int i, WaitProf& w, int slot) {
@@ -207,7 +212,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       const uint32_t tO = tmem + lane_off + 2 * kTile + t * kHeadDim;
       const int q_row = m0 + t * kTile + r;                         // local row
       const long long q_pos = (long long)p.mask.q_pos0 + q_row;     // global position
-      const float scale = p.scale_log2;
+      const float scale = p.scale_log2 * (p.scale_q ? (*p.scale_q) * (*p.scale_k) : 1.0f);
       const bool has_bias = p.mask.bias != nullptr, has_seg = p.mask.seg != nullptr;
       const float* bias_row = has_bias ? p.mask.bias + (long long)b * p.mask.bias_stride : nullptr;
       const int* seg_row = has_seg ? p.mask.seg + (long long)b * p.mask.seg_stride : nullptr;
@@ -300,8 +305,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
               e3 = ex2f(__uint_as_float(s[c][i + 3]) + neg_m);
             }
             sum0 += e0; sum1 += e1; sum2 += e2; sum3 += e3;
-            pk[i / 2] = pack_bf16x2(e0, e1);
-            pk[i / 2 + 1] = pack_bf16x2(e2, e3);
+            pk[i / 2] = kF16 ? pack_f16x2(e0, e1) : pack_bf16x2(e0, e1);
+            pk[i / 2 + 1] = kF16 ? pack_f16x2(e2, e3) : pack_bf16x2(e2, e3);
           }
           tmem_st_x16(tS + c * 16, pk);  // P (bf16) aliases the first 64 columns of S
         }
@@ -328,6 +333,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       float wa = (m_c == -INFINITY) ? 0.f : ex2f(m_c - m_new);     // weight of the carry
       float wb = (m_run == -INFINITY) ? 0.f : ex2f(m_run - m_new);  // weight of this step
       const float l_new = wa * l_c + wb * l_run;
+      if (p.scale_v) wb *= *p.scale_v;   // V was stored as v16 * scale_v
       if (p.last) {
         const float inv = l_new > 0.f ? 1.0f / l_new : 0.f;
         wa *= inv;
@@ -394,11 +400,11 @@ static bool make_qkv_tmap(CUtensorMap* tm, const void* ptr, int B, int S, int H)
 
 using namespace lwm;
 
-extern "C" int lwm_attn_fwd_step(const void* q, const void* k, const void* v, void* out, float* lse, float* acc_o,
-                                 float* acc_m, float* acc_l, int B, int H, int Sq, int Sk, int D,
-                                 long long q_pos0, long long k_pos0, int causal, const float* bias,
-                                 long long bias_stride, const int* segment_ids, long long seg_stride,
-                                 float softmax_scale, int first, int last, void* stream) {
+static int attn_fwd_launch(const void* q, const void* k, const void* v, void* out, float* lse, float* acc_o,
+                           float* acc_m, float* acc_l, int B, int H, int Sq, int Sk, int D, long long q_pos0,
+                           long long k_pos0, int causal, const float* bias, long long bias_stride,
+                           const int* segment_ids, long long seg_stride, float softmax_scale, int first, int last,
+                           const float* scale_q, const float* scale_k, const float* scale_v, void* stream) {
   if (!lwm_check_device()) return LWM_ERR_DEVICE;
   if (D != kHeadDim) return lwm_fail(LWM_ERR_SHAPE, "attn_fwd: head_dim must be 128");
   if (B <= 0 || H <= 0 || Sq <= 0 || Sk <= 0 || Sq % kTile || Sk % kTile)
@@ -422,14 +428,42 @@ extern "C" int lwm_attn_fwd_step(const void* q, const void* k, const void* v, vo
   p.lse = lse; p.acc_o = acc_o; p.acc_m = acc_m; p.acc_l = acc_l;
   p.first = first; p.last = last;
   p.prof = lwm_prof_buffer();
+  p.scale_q = scale_q; p.scale_k = scale_k; p.scale_v = scale_v;
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmemBytes) !=
-        cudaSuccess)
+    if (cudaFuncSetAttribute(attn_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmemBytes) !=
+            cudaSuccess ||
+        cudaFuncSetAttribute(attn_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmemBytes) !=
+            cudaSuccess)
       return lwm_fail(LWM_ERR_CUDA, "attn_fwd: cannot raise dynamic shared memory limit");
     attr_set = true;
   }
   dim3 grid((Sq + 2 * kTile - 1) / (2 * kTile), H, B);
-  attn_fwd_kernel<<<grid, kFwdThreads, kFwdSmemBytes, reinterpret_cast<cudaStream_t>(stream)>>>(tq, tk, tv, p);
+  if (scale_q)
+    attn_fwd_kernel<true><<<grid, kFwdThreads, kFwdSmemBytes, reinterpret_cast<cudaStream_t>(stream)>>>(tq, tk, tv, p);
+  else
+    attn_fwd_kernel<false><<<grid, kFwdThreads, kFwdSmemBytes, reinterpret_cast<cudaStream_t>(stream)>>>(tq, tk, tv, p);
   return lwm_check_launch("attn_fwd_kernel");
+}
+
+extern "C" int lwm_attn_fwd_step(const void* q, const void* k, const void* v, void* out, float* lse, float* acc_o,
+                                 float* acc_m, float* acc_l, int B, int H, int Sq, int Sk, int D,
+                                 long long q_pos0, long long k_pos0, int causal, const float* bias,
+                                 long long bias_stride, const int* segment_ids, long long seg_stride,
+                                 float softmax_scale, int first, int last, void* stream) {
+  return attn_fwd_launch(q, k, v, out, lse, acc_o, acc_m, acc_l, B, H, Sq, Sk, D, q_pos0, k_pos0, causal, bias,
+                         bias_stride, segment_ids, seg_stride, softmax_scale, first, last, nullptr, nullptr, nullptr, stream);
+}
+
+// fp16-operand variant: q/k/v are the fp16 copies made by lwm_attn_to_f16, scale_* their device scalars.
+extern "C" int lwm_attn_fwd_step_f16(const void* q16, const void* k16, const void* v16, const float* scale_q,
+                                     const float* scale_k, const float* scale_v,
+                                     void* out, float* lse, float* acc_o, float* acc_m, float* acc_l, int B, int H,
+                                     int Sq, int Sk, int D, long long q_pos0, long long k_pos0, int causal,
+                                     const float* bias, long long bias_stride, const int* segment_ids,
+                                     long long seg_stride, float softmax_scale, int first, int last, void* stream) {
+  if (!scale_q || !scale_k || !scale_v) return lwm_fail(LWM_ERR_ARG, "attn_fwd_f16: scales required");
+  return attn_fwd_launch(q16, k16, v16, out, lse, acc_o, acc_m, acc_l, B, H, Sq, Sk, D, q_pos0, k_pos0, causal, bias,
+                         bias_stride, segment_ids, seg_stride, softmax_scale, first, last, scale_q, scale_k, scale_v,
+                         stream);
 }

@@ -51,6 +51,47 @@ __global__ void add_f32_kernel(float4* __restrict__ dst, const float4* __restric
   }
 }
 
+// |x| max over a bf16 tensor as raw bits (non-negative floats order like unsigned ints)
+__global__ void absmax_bf16_kernel(const uint4* __restrict__ x, long long n8, unsigned* __restrict__ out_bits) {
+  unsigned m = 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8;
+       i += (long long)gridDim.x * blockDim.x) {
+    const uint4 v = x[i];
+    const unsigned w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      m = max(m, (w[k] & 0x7fffu) << 16);          // low bf16, sign cleared, as fp32 bits
+      m = max(m, w[k] & 0x7fff0000u);              // high bf16
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m) atomicMax(out_bits, m);
+}
+
+// x16 = fp16(x / scale) with scale = 2^(e-12), e = exponent of the tensor's |max| (scale 1 for an all-zero
+// tensor): the largest magnitude lands in [2^12, 2^13), so anything down to 2^-26 of it stays a normal fp16
+// and the conversion of every such bf16 value (8 significant bits) is exact.
+__global__ void bf16_to_scaled_f16_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, long long n8,
+                                          const unsigned* __restrict__ absmax_bits, float* __restrict__ scale_out) {
+  const unsigned bits = *absmax_bits;
+  const int e = int(bits >> 23) - 127;
+  const float inv = bits ? __uint_as_float(unsigned(127 - (e - 12)) << 23) : 1.0f;   // 2^(12-e)
+  if (blockIdx.x == 0 && threadIdx.x == 0) *scale_out = bits ? __uint_as_float(unsigned(127 + (e - 12)) << 23) : 1.0f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8;
+       i += (long long)gridDim.x * blockDim.x) {
+    const uint4 v = x[i];
+    const unsigned w[4] = {v.x, v.y, v.z, v.w};
+    unsigned o[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float lo = __uint_as_float(w[k] << 16) * inv, hi = __uint_as_float(w[k] & 0xffff0000u) * inv;
+      o[k] = pack_f16x2(lo, hi);
+    }
+    y[i] = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
 }  // namespace lwm
 
 using namespace lwm;
@@ -91,4 +132,23 @@ extern "C" int lwm_add_f32(float* dst, const float* src, long long n, void* stre
   add_f32_kernel<<<blocks, threads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<float4*>(dst), reinterpret_cast<const float4*>(src), n4);
   return lwm_check_launch("add_f32_kernel");
+}
+
+// bf16 tensor -> exact scaled fp16 copy + its power-of-two scale (device float). workspace: 4 bytes.
+extern "C" int lwm_attn_to_f16(const void* src_bf16, void* dst_f16, float* scale_out, void* workspace, long long n,
+                               void* stream) {
+  if (!lwm_check_device()) return LWM_ERR_DEVICE;
+  if (!src_bf16 || !dst_f16 || !scale_out || !workspace) return lwm_fail(LWM_ERR_ARG, "attn_to_f16: null pointer");
+  if (n <= 0 || n % 8) return lwm_fail(LWM_ERR_SHAPE, "attn_to_f16: n must be a positive multiple of 8");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (cudaMemsetAsync(workspace, 0, 4, st) != cudaSuccess) return lwm_fail(LWM_ERR_CUDA, "attn_to_f16: memset failed");
+  const long long n8 = n / 8;
+  const long long want = (n8 + 255) / 256;
+  const unsigned blocks = unsigned(want < 148LL * 8 ? want : 148LL * 8);
+  absmax_bf16_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const uint4*>(src_bf16), n8,
+                                             reinterpret_cast<unsigned*>(workspace));
+  bf16_to_scaled_f16_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const uint4*>(src_bf16),
+                                                    reinterpret_cast<uint4*>(dst_f16), n8,
+                                                    reinterpret_cast<const unsigned*>(workspace), scale_out);
+  return lwm_check_launch("attn_to_f16 kernels");
 }
