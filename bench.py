@@ -218,6 +218,7 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        os.environ.setdefault("TORCH_NCCL_HIGH_PRIORITY", "1")   # NCCL copy kernels must be able to preempt
         dist.init_process_group("nccl", device_id=dev)
     S = args.seq
     assert S % world == 0

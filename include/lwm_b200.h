@@ -85,10 +85,13 @@ int lwm_attn_bwd_step(const void* q, const void* k, const void* v, const void* d
  * higher-precision mode converts every operand once to an exact, power-of-two-scaled fp16 copy
  * (lwm_attn_to_f16: x16 = x / scale, scale = 2^(e-12) with e the exponent of the tensor's |max|) and keeps the
  * probabilities P and dS at fp16's 11 significant bits instead of bf16's 8. scale_* are DEVICE scalars written
- * by lwm_attn_to_f16; all scale factors are undone in fp32 inside the kernels. Same semantics otherwise. */
+ * by lwm_attn_to_f16; all scale factors are undone in fp32 inside the kernels. Same semantics otherwise.
+ * out_f32_or_null: un-rounded copy of `out` written on the last step, so that delta = rowsum(dO o O) of the
+ * backward (lwm_attn_bwd_prep_f32) is not limited by the bf16 rounding of `out`. */
+int lwm_attn_bwd_prep_f32(const float* out_f32, const void* dout, float* delta, int B, int H, int Sq, int D, void* stream);
 int lwm_attn_to_f16(const void* src_bf16, void* dst_f16, float* scale_out, void* workspace4, long long n, void* stream);
 int lwm_attn_fwd_step_f16(const void* q16, const void* k16, const void* v16, const float* scale_q, const float* scale_k,
-                          const float* scale_v, void* out, float* lse, float* acc_o, float* acc_m, float* acc_l, int B,
+                          const float* scale_v, float* out_f32_or_null, void* out, float* lse, float* acc_o, float* acc_m, float* acc_l, int B,
                           int H, int Sq, int Sk, int D, long long q_pos0, long long k_pos0, int causal,
                           const float* bias, long long bias_stride, const int* segment_ids, long long seg_stride,
                           float softmax_scale, int first, int last, void* stream);

@@ -29,6 +29,7 @@ struct FwdParams {
   float scale_log2;  // softmax_scale * log2(e)
   MaskParams mask;
   __nv_bfloat16* out;  // [B,Sq,H,D]   written when last
+  float* out_f32;      // optional un-rounded copy of `out` (fp16 precision mode residual), written when last
   float* lse;          // [B,H,Sq]     natural-log LSE, written when last
   float* acc_o;        // [B,Sq,H,D]   fp32 numerator carry (relative to acc_m)
   float* acc_m;        // [B,H,Sq]     running max, log2 domain
@@ -369,6 +370,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           for (int i = 0; i < 4; ++i)
             dst[i] = make_uint4(pack_bf16x2(f[8 * i], f[8 * i + 1]), pack_bf16x2(f[8 * i + 2], f[8 * i + 3]),
                                 pack_bf16x2(f[8 * i + 4], f[8 * i + 5]), pack_bf16x2(f[8 * i + 6], f[8 * i + 7]));
+          if (p.out_f32) {
+            float4* d32 = reinterpret_cast<float4*>(p.out_f32 + o_idx + c * 32);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) d32[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+          }
         } else {
           float4* dst = reinterpret_cast<float4*>(p.acc_o + o_idx + c * 32);
 #pragma unroll
@@ -404,7 +410,8 @@ static int attn_fwd_launch(const void* q, const void* k, const void* v, void* ou
                            float* acc_m, float* acc_l, int B, int H, int Sq, int Sk, int D, long long q_pos0,
                            long long k_pos0, int causal, const float* bias, long long bias_stride,
                            const int* segment_ids, long long seg_stride, float softmax_scale, int first, int last,
-                           const float* scale_q, const float* scale_k, const float* scale_v, void* stream) {
+                           const float* scale_q, const float* scale_k, const float* scale_v, float* out_f32,
+                           void* stream) {
   if (!lwm_check_device()) return LWM_ERR_DEVICE;
   if (D != kHeadDim) return lwm_fail(LWM_ERR_SHAPE, "attn_fwd: head_dim must be 128");
   if (B <= 0 || H <= 0 || Sq <= 0 || Sk <= 0 || Sq % kTile || Sk % kTile)
@@ -429,6 +436,7 @@ static int attn_fwd_launch(const void* q, const void* k, const void* v, void* ou
   p.first = first; p.last = last;
   p.prof = lwm_prof_buffer();
   p.scale_q = scale_q; p.scale_k = scale_k; p.scale_v = scale_v;
+  p.out_f32 = out_f32;
   static bool attr_set = false;
   if (!attr_set) {
     if (cudaFuncSetAttribute(attn_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmemBytes) !=
@@ -452,12 +460,12 @@ extern "C" int lwm_attn_fwd_step(const void* q, const void* k, const void* v, vo
                                  long long bias_stride, const int* segment_ids, long long seg_stride,
                                  float softmax_scale, int first, int last, void* stream) {
   return attn_fwd_launch(q, k, v, out, lse, acc_o, acc_m, acc_l, B, H, Sq, Sk, D, q_pos0, k_pos0, causal, bias,
-                         bias_stride, segment_ids, seg_stride, softmax_scale, first, last, nullptr, nullptr, nullptr, stream);
+                         bias_stride, segment_ids, seg_stride, softmax_scale, first, last, nullptr, nullptr, nullptr, nullptr, stream);
 }
 
 // fp16-operand variant: q/k/v are the fp16 copies made by lwm_attn_to_f16, scale_* their device scalars.
 extern "C" int lwm_attn_fwd_step_f16(const void* q16, const void* k16, const void* v16, const float* scale_q,
-                                     const float* scale_k, const float* scale_v,
+                                     const float* scale_k, const float* scale_v, float* out_f32,
                                      void* out, float* lse, float* acc_o, float* acc_m, float* acc_l, int B, int H,
                                      int Sq, int Sk, int D, long long q_pos0, long long k_pos0, int causal,
                                      const float* bias, long long bias_stride, const int* segment_ids,
@@ -465,5 +473,5 @@ extern "C" int lwm_attn_fwd_step_f16(const void* q16, const void* k16, const voi
   if (!scale_q || !scale_k || !scale_v) return lwm_fail(LWM_ERR_ARG, "attn_fwd_f16: scales required");
   return attn_fwd_launch(q16, k16, v16, out, lse, acc_o, acc_m, acc_l, B, H, Sq, Sk, D, q_pos0, k_pos0, causal, bias,
                          bias_stride, segment_ids, seg_stride, softmax_scale, first, last, scale_q, scale_k, scale_v,
-                         stream);
+                         out_f32, stream);
 }

@@ -33,6 +33,27 @@ __global__ void bwd_prep_kernel(const __nv_bfloat16* __restrict__ out, const __n
   }
 }
 
+// same with an fp32 `out` (fp16 precision mode keeps the un-rounded output as residual)
+__global__ void bwd_prep_f32_kernel(const float* __restrict__ out, const __nv_bfloat16* __restrict__ dout,
+                                    float* __restrict__ delta, int B, int H, int S) {
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long n_rows = (long long)B * S * H;
+  if (row >= n_rows) return;
+  const int lane = threadIdx.x & 31;
+  const float4 a = reinterpret_cast<const float4*>(out + row * kHeadDim)[lane];
+  const uint2 g = reinterpret_cast<const uint2*>(dout + row * kHeadDim)[lane];
+  const __nv_bfloat162 g0 = *reinterpret_cast<const __nv_bfloat162*>(&g.x);
+  const __nv_bfloat162 g1 = *reinterpret_cast<const __nv_bfloat162*>(&g.y);
+  float acc = a.x * __low2float(g0) + a.y * __high2float(g0) + a.z * __low2float(g1) + a.w * __high2float(g1);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) {
+    const int h = int(row % H);
+    const long long bs = row / H;
+    delta[((long long)(bs / S) * H + h) * S + (bs % S)] = acc;
+  }
+}
+
 __global__ void cast_f32_bf16_kernel(const float4* __restrict__ src, uint2* __restrict__ dst, long long n4) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
        i += (long long)gridDim.x * blockDim.x) {
@@ -106,6 +127,18 @@ extern "C" int lwm_attn_bwd_prep(const void* out, const void* dout, float* delta
   bwd_prep_kernel<<<unsigned((rows + warps - 1) / warps), warps * 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const __nv_bfloat16*>(out), reinterpret_cast<const __nv_bfloat16*>(dout), delta, B, H, Sq);
   return lwm_check_launch("bwd_prep_kernel");
+}
+
+extern "C" int lwm_attn_bwd_prep_f32(const float* out_f32, const void* dout, float* delta, int B, int H, int Sq, int D,
+                                     void* stream) {
+  if (!lwm_check_device()) return LWM_ERR_DEVICE;
+  if (D != kHeadDim) return lwm_fail(LWM_ERR_SHAPE, "attn_bwd_prep_f32: head_dim must be 128");
+  if (!out_f32 || !dout || !delta) return lwm_fail(LWM_ERR_ARG, "attn_bwd_prep_f32: null pointer");
+  const long long rows = (long long)B * Sq * H;
+  const int warps = 8;
+  bwd_prep_f32_kernel<<<unsigned((rows + warps - 1) / warps), warps * 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      out_f32, reinterpret_cast<const __nv_bfloat16*>(dout), delta, B, H, Sq);
+  return lwm_check_launch("bwd_prep_f32_kernel");
 }
 
 extern "C" int lwm_cast_f32_to_bf16(const float* src, void* dst, long long n, void* stream) {

@@ -148,12 +148,13 @@ def to_f16(x, stream=None):
 
 
 def fwd_step(q, k, v, out, lse, acc_o, acc_m, acc_l, q_pos0, k_pos0, causal, bias, seg, first, last,
-             stream=None, scales=None):
+             stream=None, scales=None, out_f32=None):
     B, Sq, H, D = q.shape
     Sk = k.shape[1]
     if scales is not None:   # fp16-operand kernels: q/k/v are fp16 copies, scales = (sq, sk, sv) device scalars
         _lib.call("lwm_attn_fwd_step_f16", _lib.ptr(q), _lib.ptr(k), _lib.ptr(v), _lib.ptr(scales[0]),
-                  _lib.ptr(scales[1]), _lib.ptr(scales[2]), _lib.ptr(out), _lib.ptr(lse), _lib.ptr(acc_o),
+                  _lib.ptr(scales[1]), _lib.ptr(scales[2]), _lib.ptr(out_f32), _lib.ptr(out), _lib.ptr(lse),
+                  _lib.ptr(acc_o),
                   _lib.ptr(acc_m), _lib.ptr(acc_l), B, H, Sq, Sk, D, int(q_pos0), int(k_pos0), int(bool(causal)),
                   _lib.ptr(bias), 0 if bias is None else bias.shape[1], _lib.ptr(seg),
                   0 if seg is None else seg.shape[1], 1.0 / math.sqrt(D), int(first), int(last),
@@ -168,6 +169,10 @@ def fwd_step(q, k, v, out, lse, acc_o, acc_m, acc_l, q_pos0, k_pos0, causal, bia
 
 def bwd_prep(out, dout, delta, stream=None):
     B, Sq, H, D = out.shape
+    if out.dtype == torch.float32:
+        _lib.call("lwm_attn_bwd_prep_f32", _lib.ptr(out), _lib.ptr(dout), _lib.ptr(delta), B, H, Sq, D,
+                  _lib.stream_ptr(stream))
+        return
     _lib.call("lwm_attn_bwd_prep", _lib.ptr(out), _lib.ptr(dout), _lib.ptr(delta), B, H, Sq, D,
               _lib.stream_ptr(stream))
 
@@ -217,6 +222,7 @@ class CudaOpsF16(CudaOps):
 
     def __init__(self):
         self._cache = {}
+        self.out_f32 = {}     # bf16 out chunk (by address) -> fp32 copy, the residual the backward's delta uses
 
     def _f16(self, x):
         key = (x.data_ptr(), tuple(x.shape))
@@ -229,13 +235,24 @@ class CudaOpsF16(CudaOps):
 
     def fwd_step(self, q, k, v, out, lse, acc_o, acc_m, acc_l, q_pos0, k_pos0, causal, bias, seg, first, last):
         (q16, sq), (k16, sk), (v16, sv) = self._f16(q), self._f16(k), self._f16(v)
+        o32 = None
+        if last:
+            o32 = torch.empty(out.shape, dtype=torch.float32, device=out.device)
+            self.out_f32[out.data_ptr()] = o32
         fwd_step(q16, k16, v16, out, lse, acc_o, acc_m, acc_l, q_pos0, k_pos0, causal, bias, seg, first, last,
-                 scales=(sq, sk, sv))
+                 scales=(sq, sk, sv), out_f32=o32)
 
     def bwd_step(self, q, k, v, dout, lse, delta, dq_acc, dk_acc, dv_acc, q_pos0, k_pos0, causal, bias, seg):
         (q16, sq), (k16, sk), (v16, sv), (d16, sd) = self._f16(q), self._f16(k), self._f16(v), self._f16(dout)
         bwd_step(q16, k16, v16, d16, lse, delta, dq_acc, dk_acc, dv_acc, q_pos0, k_pos0, causal, bias, seg,
                  scales=(sq, sk, sv, sd))
+
+
+def _f32_residuals(ops, res):
+    """fp16 precision mode: the backward's delta = rowsum(dO o O) is taken from the un-rounded fp32 output."""
+    if isinstance(ops, CudaOpsF16):
+        res["out_chunks"] = [ops.out_f32.get(o.data_ptr(), o) for o in res["out_chunks"]]
+    return res
 
 
 def _ops_for(precision):
@@ -250,9 +267,10 @@ def ring_forward(q, k, v, bias, seg, causal, group, rank, world, layout="auto", 
         out = torch.empty_like(q)
         lse = torch.empty((B, H, Sq), dtype=torch.float32, device=q.device)
         ops.fwd_step(q, k, v, out, lse, None, None, None, 0, 0, causal, bias, seg, True, True)
-        return out, dict(q_chunks=[q], out_chunks=[out], lse_chunks=[lse])
+        return out, _f32_residuals(ops, dict(q_chunks=[q], out_chunks=[out], lse_chunks=[lse]))
     plan = rs.make_plan(world, rank, Sq, k.shape[1], causal, layout)
-    return rx.run_forward(plan, q, k, v, bias, seg, causal, group, ops)
+    out, res = rx.run_forward(plan, q, k, v, bias, seg, causal, group, ops)
+    return out, _f32_residuals(ops, res)
 
 
 def ring_backward(res, k, v, dout, bias, seg, causal, group, rank, world, layout="auto", precision="bf16"):
