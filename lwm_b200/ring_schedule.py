@@ -85,16 +85,35 @@ def compute_chunks(world, rank, Sq, layout):
     return [QRef(c // 2, (c % 2) * h, h, c * h) for c in (rank, 2 * world - 1 - rank)]
 
 
-def step_kv(world, rank, idx, Sk, layout):
-    """K/V blocks rank `rank` consumes at step idx (before visibility filtering)."""
+def step_kv(world, rank, idx, Sk, layout, sub=(0, 1)):
+    """K/V blocks rank `rank` consumes at step idx (before visibility filtering). sub=(j, n): only the
+    j-th of n equal row pieces of every block (sub-block pipelining of a step)."""
     src = (rank - idx) % world
     if layout == "contiguous":
-        return [KvRef(src, 0, Sk, src * Sk)]
-    h = Sk // 2
-    return [KvRef(c // 2, (c % 2) * h, h, c * h) for c in (src, 2 * world - 1 - src)]
+        blocks = [KvRef(src, 0, Sk, src * Sk)]
+    else:
+        h = Sk // 2
+        blocks = [KvRef(c // 2, (c % 2) * h, h, c * h) for c in (src, 2 * world - 1 - src)]
+    j, n = sub
+    if n == 1:
+        return blocks
+    return [KvRef(b.owner, b.start + j * (b.length // n), b.length // n, b.pos0 + j * (b.length // n)) for b in blocks]
 
 
-def make_plan(world, rank, Sq, Sk, causal, layout="auto"):
+def auto_sub(world, Sk, layout, min_piece=2048):
+    """How many pieces to cut the first / last step's blocks into so that their transfer pipelines with the
+    tile kernels instead of being exposed (nothing precedes step 0; nothing follows the last dK/dV return)."""
+    if world == 1:
+        return 1
+    block = Sk if layout == "contiguous" else Sk // 2
+    n = 1
+    while n < 4 and block % (2 * n * 128) == 0 and block // (2 * n) >= min_piece:
+        n *= 2
+    return n
+
+
+def make_plan(world, rank, Sq, Sk, causal, layout="auto", n_sub_first=1, n_sub_last=1):
+    """n_sub_first / n_sub_last: split step 0 / step world-1 into that many sub-steps (same on every rank)."""
     layout = choose_layout(world, Sq, Sk, causal, layout)
     q_chunks = compute_chunks(world, rank, Sq, layout)
     # rows of my contiguous shard that another rank computes
@@ -107,21 +126,25 @@ def make_plan(world, rank, Sq, Sk, causal, layout="auto"):
                 q_sends.append((qc.start, qc.length, peer))
     steps = []
     for idx in range(world):
-        st = Step()
-        for kv in step_kv(world, rank, idx, Sk, layout):
-            needed = [qi for qi, qc in enumerate(q_chunks) if visible(qc.pos0, qc.length, kv.pos0, causal)]
-            if needed:
-                st.kv.append(kv)
-                st.pairs.extend((qi, len(st.kv) - 1) for qi in needed)
-        # what do the OTHER ranks need from my shard at this step?
-        for peer in range(world):
-            if peer == rank:
-                continue
-            peer_q = compute_chunks(world, peer, Sq, layout)
-            for kv in step_kv(world, peer, idx, Sk, layout):
-                if kv.owner == rank and any(visible(qc.pos0, qc.length, kv.pos0, causal) for qc in peer_q):
-                    st.sends.append((kv.start, kv.length, peer))
-        steps.append(st)
+        n_sub = n_sub_first if idx == 0 else (n_sub_last if idx == world - 1 else 1)
+        if world == 1:
+            n_sub = 1
+        for j in range(n_sub):
+            st = Step()
+            for kv in step_kv(world, rank, idx, Sk, layout, (j, n_sub)):
+                needed = [qi for qi, qc in enumerate(q_chunks) if visible(qc.pos0, qc.length, kv.pos0, causal)]
+                if needed:
+                    st.kv.append(kv)
+                    st.pairs.extend((qi, len(st.kv) - 1) for qi in needed)
+            # what do the OTHER ranks need from my shard at this (sub-)step?
+            for peer in range(world):
+                if peer == rank:
+                    continue
+                peer_q = compute_chunks(world, peer, Sq, layout)
+                for kv in step_kv(world, peer, idx, Sk, layout, (j, n_sub)):
+                    if kv.owner == rank and any(visible(qc.pos0, qc.length, kv.pos0, causal) for qc in peer_q):
+                        st.sends.append((kv.start, kv.length, peer))
+            steps.append(st)
     return Plan(world, rank, layout, q_chunks, q_sends, steps)
 
 

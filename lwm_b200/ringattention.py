@@ -268,7 +268,8 @@ def ring_forward(q, k, v, bias, seg, causal, group, rank, world, layout="auto", 
         lse = torch.empty((B, H, Sq), dtype=torch.float32, device=q.device)
         ops.fwd_step(q, k, v, out, lse, None, None, None, 0, 0, causal, bias, seg, True, True)
         return out, _f32_residuals(ops, dict(q_chunks=[q], out_chunks=[out], lse_chunks=[lse]))
-    plan = rs.make_plan(world, rank, Sq, k.shape[1], causal, layout)
+    lay = rs.choose_layout(world, Sq, k.shape[1], causal, layout)
+    plan = rs.make_plan(world, rank, Sq, k.shape[1], causal, lay, n_sub_first=rs.auto_sub(world, k.shape[1], lay))
     out, res = rx.run_forward(plan, q, k, v, bias, seg, causal, group, ops)
     return out, _f32_residuals(ops, res)
 
@@ -291,5 +292,7 @@ def ring_backward(res, k, v, dout, bias, seg, causal, group, rank, world, layout
         cast_f32_to_bf16(dk_acc, dk)
         cast_f32_to_bf16(dv_acc, dv)
         return dq, dk, dv
-    plan = rs.make_plan(world, rank, dout.shape[1], Sk, causal, layout)
+    lay = rs.choose_layout(world, dout.shape[1], Sk, causal, layout)
+    n_sub = rs.auto_sub(world, Sk, lay)
+    plan = rs.make_plan(world, rank, dout.shape[1], Sk, causal, lay, n_sub_first=n_sub, n_sub_last=n_sub)
     return rx.run_backward(plan, res, k, v, dout, bias, seg, causal, group, ops)

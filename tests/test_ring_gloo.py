@@ -16,7 +16,7 @@ import torch.multiprocessing as mp
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _worker(rank, world, port, layout, use_masks, ret):
+def _worker(rank, world, port, layout, use_masks, ret, n_sub=1):
     sys.path.insert(0, ROOT)
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -26,7 +26,7 @@ def _worker(rank, world, port, layout, use_masks, ret):
         from oracle.step_ops import CpuOps
         from oracle.attn_dense import attention_dense, attention_dense_grads, finfo_min
         torch.manual_seed(0)
-        B, S, H, D = 1, 256 * world, 2, 16   # shard length divisible by 256 (zigzag half-chunks of 128)
+        B, S, H, D = 1, 256 * world * n_sub, 2, 16   # zigzag half-chunks of 128 * n_sub rows
         Sl = S // world
         g = torch.Generator().manual_seed(42)
         q, k, v, do = [torch.randn(B, S, H, D, generator=g) for _ in range(4)]
@@ -39,9 +39,10 @@ def _worker(rank, world, port, layout, use_masks, ret):
             do = do.clone()
             do[:, :37] = 0
         sl = slice(rank * Sl, (rank + 1) * Sl)
-        plan = rs.make_plan(world, rank, Sl, Sl, True, layout)
+        plan = rs.make_plan(world, rank, Sl, Sl, True, layout, n_sub_first=n_sub)
         out, res = rx.run_forward(plan, q[:, sl].contiguous(), k[:, sl].contiguous(), v[:, sl].contiguous(), bias,
                                   seg, True, None, CpuOps)
+        plan = rs.make_plan(world, rank, Sl, Sl, True, layout, n_sub_first=n_sub, n_sub_last=n_sub)
         dq, dk, dv = rx.run_backward(plan, res, k[:, sl].contiguous(), v[:, sl].contiguous(),
                                      do[:, sl].contiguous(), bias, seg, True, None, CpuOps)
         kw = dict(causal=True, attn_bias=None if bias is None else bias.numpy(),
@@ -84,6 +85,17 @@ def test_ring_schedules_match_dense_oracle(world, layout, use_masks):
             assert e < 1e-5, (r, ret[r])
 
 
+@pytest.mark.parametrize("world,layout", [(2, "zigzag"), (4, "zigzag"), (2, "contiguous")])
+def test_sub_step_pipelined_plans_match_dense_oracle(world, layout):
+    """first/last step cut in 2 sub-steps (transfer of piece j+1 overlaps the kernels of piece j)"""
+    ret = mp.Manager().dict()
+    mp.spawn(_worker, args=(world, _free_port(), layout, True, ret, 2), nprocs=world, join=True)
+    assert len(ret) == world
+    for r in range(world):
+        for e in ret[r]:
+            assert e < 1e-5, (r, ret[r])
+
+
 def test_zigzag_plan_is_balanced_and_consistent():
     sys.path.insert(0, ROOT)
     from lwm_b200 import ring_schedule as rs
@@ -93,10 +105,13 @@ def test_zigzag_plan_is_balanced_and_consistent():
         flat = [w for ws in per_step for w in ws]
         assert max(flat) == min(flat)                       # identical causal work, every rank, every step
         # every send has exactly one matching receive
-        for idx in range(P):
-            sends = sorted((r, peer, s, l) for r, p in enumerate(plans) for (s, l, peer) in p.steps[idx].sends)
-            recvs = sorted((kv.owner, r, kv.start, kv.length) for r, p in enumerate(plans)
-                           for kv in p.steps[idx].kv if kv.owner != r)
-            assert sends == recvs
+        for n_sub in (1, 2):
+            pl = plans if n_sub == 1 else [rs.make_plan(P, r, 1024, 1024, True, "zigzag", 2, 2) for r in range(P)]
+            assert len({len(p.steps) for p in pl}) == 1
+            for idx in range(len(pl[0].steps)):
+                sends = sorted((r, peer, s, l) for r, p in enumerate(pl) for (s, l, peer) in p.steps[idx].sends)
+                recvs = sorted((kv.owner, r, kv.start, kv.length) for r, p in enumerate(pl)
+                               for kv in p.steps[idx].kv if kv.owner != r)
+                assert sends == recvs
         contiguous = [sum(rs.work_units(rs.make_plan(P, r, 1024, 1024, True, "contiguous"), True)) for r in range(P)]
         assert max(contiguous) / (sum(contiguous) / P) > 1.4   # the imbalance zigzag removes
