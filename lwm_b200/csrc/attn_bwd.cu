@@ -327,11 +327,14 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       wp.wait(&bars.q_full[st], (it >> 1) & 1, 0);  // lse / delta of this Q tile are in smem
       wp.wait(&bars.s_full, it & 1, 1);
       tc_fence_after();
+      const long long tA0 = wp.on ? clock64() : 0;
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {
         uint32_t s[32];
+        const long long tl0 = wp.on ? clock64() : 0;
         tmem_ld_x32(tR0 + hh * 32, s);
         tmem_wait_ld();
+        if (wp.on) wp.acc[3] += clock64() - tl0;
         const float4* lse4 = reinterpret_cast<const float4*>(&s_lse[st][wg * 64 + hh * 32]);
 #pragma unroll
         for (int c4 = 0; c4 < 8; ++c4) {
@@ -358,10 +361,15 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       uint32_t pk[32];
 #pragma unroll
       for (int i = 0; i < 32; ++i) pk[i] = kF16 ? pack_f16x2(pr[2 * i], pr[2 * i + 1]) : pack_bf16x2(pr[2 * i], pr[2 * i + 1]);
+      const long long ts0 = wp.on ? clock64() : 0;
       tmem_st_x32(tR0, pk);
       tmem_wait_st();
       tc_fence_before();
       mbar_arrive(&bars.p_ready);
+      if (wp.on) {
+        wp.acc[4] += clock64() - ts0;
+        wp.acc[5] += clock64() - tA0;
+      }
     };
 
     // B) dS^T = P^T o (dP^T - delta) * scale  -> smem (bf16, 128B-swizzled K-major tile)
@@ -369,11 +377,14 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       const int st = it & 1;
       wp.wait(&bars.dp_full, it & 1, 2);
       tc_fence_after();
+      const long long tB0 = wp.on ? clock64() : 0;
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {
         uint32_t d[32];
+        const long long tl0 = wp.on ? clock64() : 0;
         tmem_ld_x32(tR1 + hh * 32, d);
         tmem_wait_ld();
+        if (wp.on) wp.acc[6] += clock64() - tl0;
         const float4* dl4 = reinterpret_cast<const float4*>(&s_delta[st][wg * 64 + hh * 32]);
 #pragma unroll
         for (int c16 = 0; c16 < 4; ++c16) {  // 8 bf16 (16 B) per store
@@ -397,6 +408,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
       fence_proxy_async_smem();
       mbar_arrive(&bars.ds_ready);
+      if (wp.on) wp.acc[7] += clock64() - tB0;
     };
 
     phase_a(0);
@@ -404,7 +416,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       phase_b(it);
       if (it + 1 < nq) phase_a(it + 1);   // overlaps the dK(it), dQ(it) UMMAs
     }
-    wp.flush(8, 3, clock64() - t_start);
+    // prof slots 8..10 waits (q_full, s_full, dp_full); 11,12: A tmem-ld, A st+arrive; 13: A total; 14: B tmem-ld; 15: B total
+    if (wp.on) {
+      for (int i = 0; i < 8; ++i) wp.buf[8 + i] = (unsigned long long)wp.acc[i];
+      wp.buf[20] = (unsigned long long)(clock64() - t_start);
+    }
     // ------------------------------------------------------------------ epilogue: dK (wg 0) / dV (wg 1)
     mbar_wait(&bars.final_bar, 0);
     tc_fence_after();

@@ -20,6 +20,7 @@ Two schedules, identical inputs/outputs (contiguous sequence shards, lwm/llama.p
 The plan is a pure function of (world, rank, sizes, causal, layout): every rank derives the
 same global picture, so sends and receives always match without negotiation.
 """
+import os
 from dataclasses import dataclass, field
 from typing import List, Tuple
 
@@ -103,7 +104,9 @@ def step_kv(world, rank, idx, Sk, layout, sub=(0, 1)):
 def auto_sub(world, Sk, layout, min_piece=2048):
     """How many pieces to cut the first / last step's blocks into so that their transfer pipelines with the
     tile kernels instead of being exposed (nothing precedes step 0; nothing follows the last dK/dV return)."""
-    if world == 1:
+    # measured (profiles/ring_timeline_n2_substeps_r01.log): at N=2 the extra, smaller launches cost more than the
+    # ~3 ms of exposed transfer they hide, so sub-stepping is opt-in (LWM_RING_SUBSTEPS=1)
+    if world == 1 or os.environ.get("LWM_RING_SUBSTEPS", "0") != "1":
         return 1
     block = Sk if layout == "contiguous" else Sk // 2
     n = 1

@@ -27,8 +27,10 @@ tot = b[6]
 print(" MMA issuer total %d cyc = %.0f cyc/iter" % (tot, tot / n_it))
 for i, nme in enumerate(names):
     print("   wait %-12s %9d  (%.0f/iter, %.1f%%)" % (nme, b[i], b[i] / n_it, 100.0 * b[i] / max(tot, 1)))
-tot = b[11]
+tot = b[20]
 print(" compute thread0 total %d = %.0f/iter; waits q_full %.0f s_full %.0f dp_full %.0f per iter" % (tot, tot / n_it, b[8] / n_it, b[9] / n_it, b[10] / n_it))
+print("   phase A (exp) %.0f/iter of which tmem-ld+wait %.0f, pack+tmem-st+arrive %.0f ; phase B (dS) %.0f/iter of which tmem-ld+wait %.0f" % (
+    b[13] / n_it, b[11] / n_it, b[12] / n_it, b[15] / n_it, b[14] / n_it))
 print(" drain issuer total %d = %.0f/iter; wait dq_full %.0f/iter" % (b[17], b[17] / n_it, b[16] / n_it))
 # fwd: CTA (0,0,0) = last q pair => n_kv = S/128 tiles
 tot = b[36]
