@@ -102,6 +102,20 @@ int lwm_attn_bwd_step_f16(const void* q16, const void* k16, const void* v16, con
                           long long bias_stride, const int* segment_ids, long long seg_stride, float softmax_scale,
                           void* stream);
 
+/* Decode-time attention — the reference's `ringattention_inference(q, k, v, attn_mask, axis_name)` (call site
+ * lwm/llama.py:601-614): a few query rows against this rank's KV-cache shard with an
+ * explicit boolean mask [B,1,Q,K_global] (nonzero = attend; masked logits take finfo.min semantics).
+ * lwm_attn_decode_partial reduces the local shard to one partial per (b, q, h): numerator o_part [B*Q*H,128] fp32 and
+ * ml_part [B*Q*H,2] = (max in the log2 domain, denominator); lwm_attn_decode_merge folds n_part partials (the
+ * all-gathered per-rank partials, laid out [row][n_part]) into out (bf16 [B,Q,H,128]) and lse [B*Q*H].
+ * workspace >= splits * B*Q*H * 130 floats. HBM-bound: K and V are streamed exactly once. */
+int lwm_attn_decode_partial(const void* q, const void* k, const void* v, const unsigned char* mask, float* o_part,
+                            float* ml_part, void* workspace, int B, int H, int Q, int Sk, int D, long long k_pos0,
+                            long long mask_stride_b, long long mask_stride_q, int splits, float softmax_scale,
+                            void* stream);
+int lwm_attn_decode_merge(const float* o_parts, const float* ml_parts, int n_part, void* out, float* lse,
+                          long long rows, void* stream);
+
 /* Element-wise helpers used by the ring host loop. */
 int lwm_cast_f32_to_bf16(const float* src, void* dst, long long n, void* stream);
 /* dst[i] += src[i] (fp32, n % 4 == 0): folds a dK/dV partial received from a peer into the owner's accumulator. */

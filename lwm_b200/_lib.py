@@ -25,6 +25,8 @@ _SIGNATURES = {
                                                              c_float, c_int, c_int, c_void_p],
     "lwm_attn_bwd_step_f16": [c_void_p] * 13 + [c_int] * 5 + [c_ll, c_ll, c_int, c_void_p, c_ll, c_void_p, c_ll,
                                                              c_float, c_void_p],
+    "lwm_attn_decode_partial": [c_void_p] * 7 + [c_int] * 5 + [c_ll, c_ll, c_ll, c_int, c_float, c_void_p],
+    "lwm_attn_decode_merge": [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_ll, c_void_p],
     "lwm_cast_f32_to_bf16": [c_void_p, c_void_p, c_ll, c_void_p],
     "lwm_add_f32": [c_void_p, c_void_p, c_ll, c_void_p],
     "lwm_debug_set_prof": [c_void_p],

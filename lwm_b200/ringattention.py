@@ -296,3 +296,61 @@ def ring_backward(res, k, v, dout, bias, seg, causal, group, rank, world, layout
     n_sub = rs.auto_sub(world, Sk, lay)
     plan = rs.make_plan(world, rank, dout.shape[1], Sk, causal, lay, n_sub_first=n_sub, n_sub_last=n_sub)
     return rx.run_backward(plan, res, k, v, dout, bias, seg, causal, group, ops)
+
+
+# ------------------------------------------------------------------------------------------------
+# decode path: ringattention_inference (lwm/llama.py:601-614)
+# ------------------------------------------------------------------------------------------------
+def decode_partial(q, k, v, mask_u8, k_pos0, stream=None):
+    """This rank's partial over its KV shard -> (o_part [B*Q*H,128] fp32, ml_part [B*Q*H,2] fp32)."""
+    B, Q, H, D = q.shape
+    Sk = k.shape[1]
+    rows = B * Q * H
+    splits = max(1, min(256, (Sk + 2047) // 2048))
+    o_part = torch.empty(rows, D, dtype=torch.float32, device=q.device)
+    ml_part = torch.empty(rows, 2, dtype=torch.float32, device=q.device)
+    ws = torch.empty(splits * rows * (D + 2), dtype=torch.float32, device=q.device)
+    sb = sq = 0
+    if mask_u8 is not None:
+        sb, sq = mask_u8.stride(0), mask_u8.stride(-2)
+    _lib.call("lwm_attn_decode_partial", _lib.ptr(q), _lib.ptr(k), _lib.ptr(v), _lib.ptr(mask_u8), _lib.ptr(o_part),
+              _lib.ptr(ml_part), _lib.ptr(ws), B, H, Q, Sk, D, int(k_pos0), int(sb), int(sq), splits,
+              1.0 / math.sqrt(D), _lib.stream_ptr(stream))
+    return o_part, ml_part
+
+
+def ringattention_inference(q, k, v, attn_mask, axis_name="sp"):
+    """Drop-in for the reference's decode-time op (bound at lwm/llama.py:601-614 inside shard_map):
+    q [B,Q,H,D] (replicated along the ring when Q == 1, lwm/llama.py:598), k/v [B,S_loc,H,D] = this rank's
+    contiguous shard of the KV cache, attn_mask boolean [B,1,Q,K_global] (not sharded). Returns [B,Q,H,D].
+    The reference rotates K/V around the ring for one un-chunked online-softmax tile per step; here every rank
+    reduces its own shard (K/V are read once, from local HBM) and the P partial (o, lse) pairs — a few KB — are
+    all-gathered and merged."""
+    if not q.is_cuda:
+        raise _lib.LwmError("ringattention_inference: tensors must live on an sm_100 GPU (no CPU fallback)")
+    if q.dtype != torch.bfloat16 or k.dtype != torch.bfloat16 or v.dtype != torch.bfloat16:
+        raise TypeError("ringattention_inference: q, k, v must be bfloat16")
+    group, rank, world = _resolve_group(axis_name)
+    B, Q, H, D = q.shape
+    Sk = k.shape[1]
+    mask = None
+    if attn_mask is not None:
+        if attn_mask.dim() != 4 or attn_mask.shape[1] != 1 or attn_mask.shape[2] != Q:
+            raise ValueError("attn_mask must be [B,1,Q,K_global] (lwm/llama.py:585-590)")
+        if attn_mask.shape[-1] < (rank + 1) * Sk:
+            raise ValueError("attn_mask covers %d keys but the ring holds %d" % (attn_mask.shape[-1], world * Sk))
+        mask = attn_mask.to(torch.uint8).expand(B, 1, Q, attn_mask.shape[-1]).contiguous()
+    o_part, ml_part = decode_partial(q.contiguous(), k.contiguous(), v.contiguous(), mask, rank * Sk)
+    rows = B * Q * H
+    if world > 1:
+        o_all = torch.empty(world, rows, D, dtype=torch.float32, device=q.device)
+        ml_all = torch.empty(world, rows, 2, dtype=torch.float32, device=q.device)
+        dist.all_gather_into_tensor(o_all, o_part, group=group)
+        dist.all_gather_into_tensor(ml_all, ml_part, group=group)
+        o_part = o_all.permute(1, 0, 2).contiguous()       # [row][rank][D]
+        ml_part = ml_all.permute(1, 0, 2).contiguous()
+    out = torch.empty(B, Q, H, D, dtype=torch.bfloat16, device=q.device)
+    lse = torch.empty(rows, dtype=torch.float32, device=q.device)
+    _lib.call("lwm_attn_decode_merge", _lib.ptr(o_part), _lib.ptr(ml_part), world, _lib.ptr(out), _lib.ptr(lse), rows,
+              _lib.stream_ptr())
+    return out

@@ -91,3 +91,19 @@ def attention_dense_grads(q, k, v, dout, **kw):
     dq = np.einsum("bhqk,bkhd->bqhd", ds, k) / np.sqrt(D)
     dk = np.einsum("bhqk,bqhd->bkhd", ds, q) / np.sqrt(D)
     return dq, dk, dv
+
+
+def attention_inference_dense(q, k, v, attn_mask, mask_value=None):
+    """`ringattention_inference` semantics (call site lwm/llama.py:601-614):
+    q [B,Q,H,D], k/v [B,K,H,D] (the whole, un-sharded cache), attn_mask bool [B,1,Q,K]:
+    s = where(mask, q.k/sqrt(D), finfo.min); out = softmax(s) v. float64."""
+    q = np.asarray(q, dtype=np.float64)
+    k = np.asarray(k, dtype=np.float64)
+    v = np.asarray(v, dtype=np.float64)
+    mv = finfo_min("bf16") if mask_value is None else mask_value
+    s = np.einsum("bqhd,bkhd->bhqk", q, k) / np.sqrt(q.shape[-1])
+    if attn_mask is not None:
+        s = np.where(np.asarray(attn_mask, dtype=bool), s, mv)
+    m = s.max(axis=-1, keepdims=True)
+    p = np.exp(s - m)
+    return np.einsum("bhqk,bkhd->bqhd", p / p.sum(axis=-1, keepdims=True), v)

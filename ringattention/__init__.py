@@ -1,5 +1,5 @@
 """Import shim: `from ringattention import ringattention` (lwm/llama.py:30) resolves to the B200 op."""
-from lwm_b200.ringattention import ringattention, set_axis_group  # noqa: F401
+from lwm_b200.ringattention import ringattention, ringattention_inference, set_axis_group  # noqa: F401
 
 
 def _not_built(name):
@@ -9,6 +9,5 @@ def _not_built(name):
     return f
 
 
-ringattention_inference = _not_built("ringattention_inference")
 blockwise_feedforward = _not_built("blockwise_feedforward")
 ringattention_jax = ringattention

@@ -60,6 +60,22 @@ def main():
             worst = max(worst, *errs)
             print("rank %d layout=%s masks=%s errs(out,dq,dk,dv)=%s" % (rank, layout, masks,
                                                                          ["%.2e" % e for e in errs]), flush=True)
+    # decode path: every rank holds a KV-cache shard, the single query row is replicated
+    from lwm_b200.ringattention import ringattention_inference
+    g2 = torch.Generator().manual_seed(7)
+    qd = torch.randn(B, 1, H, D, generator=g2).to(torch.bfloat16).to(dev)
+    maskd = torch.ones(B, 1, 1, S, dtype=torch.bool)
+    maskd[..., :29] = False
+    maskd[..., S - 5:] = False
+    od = ringattention_inference(qd, k[:, sl].contiguous(), v[:, sl].contiguous(), maskd.to(dev), axis_name="sp")
+    saved = ra._resolve_group
+    ra._resolve_group = lambda axis: (None, 0, 1)
+    od_ref = ringattention_inference(qd, k, v, maskd.to(dev), axis_name="sp")
+    ra._resolve_group = saved
+    torch.cuda.synchronize()
+    e = float((od.float() - od_ref.float()).norm() / od_ref.float().norm())
+    print("rank %d decode (ringattention_inference) err vs single-GPU = %.2e" % (rank, e), flush=True)
+    worst = max(worst, e)
     t = torch.tensor([worst], device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dist.destroy_process_group()
