@@ -283,9 +283,10 @@ def main():
         dv = torch.zeros_like(dq)
         ra.fwd_step(q, k, v, out, lse, None, None, None, 0, 0, True, None, None, True, True)
         ra.bwd_prep(out, do, delta)
+        nlse2 = ra.lse_for_bwd(lse)
         for name, fn in (("fwd", lambda: ra.fwd_step(q, k, v, out, lse, None, None, None, 0, 0, True, None, None,
                                                      True, True)),
-                         ("bwd", lambda: ra.bwd_step(q, k, v, do, lse, delta, dq, dk, dv, 0, 0, True, None, None))):
+                         ("bwd", lambda: ra.bwd_step(q, k, v, do, nlse2, delta, dq, dk, dv, 0, 0, True, None, None))):
             fn()
             torch.cuda.synchronize()
             a, b2 = ev(), ev()

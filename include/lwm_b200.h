@@ -67,6 +67,8 @@ int lwm_attn_fwd_step(const void* q, const void* k, const void* v, void* out, fl
 
 /* Ring attention, backward.
  * lwm_attn_bwd_prep: delta[b,h,s] = sum_d dout[b,s,h,d] * out[b,s,h,d]  (fp32), once per backward.
+ * lwm_attn_bwd_lse:  nlse2[i] = -lse[i]*log2(e) (-inf for rows whose lse is at the masked level), once per backward;
+ *                    lwm_attn_bwd_step takes THIS array as its `lse` argument (the per-tile kernel is exp-bound).
  * lwm_attn_bwd_step: one ring step of the reference's custom_vjp bwd (SURVEY.md Appendix A `bwd`):
  *   recomputes P from (q, k, lse), accumulates
  *     dq_acc [B,Sq,H,D] fp32 += dS K / sqrt(D)        (atomic fp32 tile reductions; zero it first)
@@ -75,6 +77,7 @@ int lwm_attn_fwd_step(const void* q, const void* k, const void* v, void* out, fl
  *   dk_acc/dv_acc travel with the K/V block around the ring exactly like the reference's dk, dv.
  */
 int lwm_attn_bwd_prep(const void* out, const void* dout, float* delta, int B, int H, int Sq, int D, void* stream);
+int lwm_attn_bwd_lse(const float* lse, float* nlse2, long long n, void* stream);
 int lwm_attn_bwd_step(const void* q, const void* k, const void* v, const void* dout, const float* lse,
                       const float* delta, float* dq_acc, float* dk_acc, float* dv_acc, int B, int H, int Sq,
                       int Sk, int D, long long q_pos0, long long k_pos0, int causal, const float* bias,

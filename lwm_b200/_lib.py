@@ -17,6 +17,7 @@ _SIGNATURES = {
     "lwm_attn_fwd_step": [c_void_p] * 8 + [c_int] * 5 + [c_ll, c_ll, c_int, c_void_p, c_ll, c_void_p, c_ll,
                                                        c_float, c_int, c_int, c_void_p],
     "lwm_attn_bwd_prep": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
+    "lwm_attn_bwd_lse": [c_void_p, c_void_p, c_ll, c_void_p],
     "lwm_attn_bwd_step": [c_void_p] * 9 + [c_int] * 5 + [c_ll, c_ll, c_int, c_void_p, c_ll, c_void_p, c_ll,
                                                        c_float, c_void_p],
     "lwm_attn_to_f16": [c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_void_p],

@@ -36,7 +36,7 @@ struct BwdParams {
   float scale;       // softmax_scale
   float scale_log2;  // softmax_scale * log2(e)
   MaskParams mask;
-  const float* lse;    // [B,H,Sq] natural log
+  const float* lse;    // [B,H,Sq] PRE-SCALED: -lse*log2(e) (lwm_attn_bwd_lse), -inf for rows without any unmasked key
   const float* delta;  // [B,H,Sq]
   float* dk_acc;       // [B,Sk,H,D] fp32
   float* dv_acc;       // [B,Sk,H,D] fp32
@@ -343,9 +343,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const int c = c4 * 4 + e;
-            // lse at the masked level (row never saw an unmasked key; padded rows in the reference):
-            // fp32 cannot resolve logits against it, so such rows get p = 0, i.e. no gradient
-            const float nl2 = (ls[e] < -1.0e29f) ? -INFINITY : -ls[e] * kLog2e;
+            // ls = -lse*log2e, or -inf for rows at the masked level (p = 0, no gradient): lwm_attn_bwd_lse
+            const float nl2 = ls[e];
             float tv = __uint_as_float(s[c]) * scale_log2;
             if (need_mask) {
               tv = key_masked ? kMaskedLogit : tv + bias_t;

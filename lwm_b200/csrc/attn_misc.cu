@@ -54,6 +54,16 @@ __global__ void bwd_prep_f32_kernel(const float* __restrict__ out, const __nv_bf
   }
 }
 
+// nlse2 = -lse * log2(e), with rows whose lse sits at the masked level (never saw an unmasked key: padded rows)
+// mapped to -inf so that the backward gives them p = 0 — hoisted out of the tile kernel, where every key-tile CTA
+// would redo it for every query column.
+__global__ void lse_to_nlse2_kernel(const float* __restrict__ lse, float* __restrict__ nlse2, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float l = lse[i];
+    nlse2[i] = (l < -1.0e29f) ? -INFINITY : -l * kLog2e;
+  }
+}
+
 __global__ void cast_f32_bf16_kernel(const float4* __restrict__ src, uint2* __restrict__ dst, long long n4) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
        i += (long long)gridDim.x * blockDim.x) {
@@ -139,6 +149,15 @@ extern "C" int lwm_attn_bwd_prep_f32(const float* out_f32, const void* dout, flo
   bwd_prep_f32_kernel<<<unsigned((rows + warps - 1) / warps), warps * 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       out_f32, reinterpret_cast<const __nv_bfloat16*>(dout), delta, B, H, Sq);
   return lwm_check_launch("bwd_prep_f32_kernel");
+}
+
+extern "C" int lwm_attn_bwd_lse(const float* lse, float* nlse2, long long n, void* stream) {
+  if (!lwm_check_device()) return LWM_ERR_DEVICE;
+  if (!lse || !nlse2 || n <= 0) return lwm_fail(LWM_ERR_ARG, "attn_bwd_lse: bad args");
+  const long long want = (n + 255) / 256;
+  lse_to_nlse2_kernel<<<unsigned(want < 148LL * 8 ? want : 148LL * 8), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      lse, nlse2, n);
+  return lwm_check_launch("lse_to_nlse2_kernel");
 }
 
 extern "C" int lwm_cast_f32_to_bf16(const float* src, void* dst, long long n, void* stream) {

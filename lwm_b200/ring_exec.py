@@ -227,6 +227,7 @@ def run_backward(plan, res, k, v, dout, bias, seg, causal, group, ops):
     dq_acc = [torch.zeros(c.shape, dtype=torch.float32, device=dev) for c in q_chunks]
     for qi in range(n_q):
         ops.bwd_prep(out_chunks[qi], do_chunks[qi], delta[qi])
+    lse_chunks = [ops.lse_for_bwd(l) for l in lse_chunks]   # pre-scaled once; the tile kernel is exp-bound
     dk_acc = torch.zeros(k.shape, dtype=torch.float32, device=dev)
     dv_acc = torch.zeros(v.shape, dtype=torch.float32, device=dev)
 

@@ -177,8 +177,16 @@ def bwd_prep(out, dout, delta, stream=None):
               _lib.stream_ptr(stream))
 
 
+def lse_for_bwd(lse, stream=None):
+    """-lse*log2(e) (masked-level rows -> -inf), computed once per backward: what bwd_step takes as `lse`."""
+    out = torch.empty_like(lse)
+    _lib.call("lwm_attn_bwd_lse", _lib.ptr(lse), _lib.ptr(out), lse.numel(), _lib.stream_ptr(stream))
+    return out
+
+
 def bwd_step(q, k, v, dout, lse, delta, dq_acc, dk_acc, dv_acc, q_pos0, k_pos0, causal, bias, seg, stream=None,
              scales=None):
+    """`lse` is the PRE-SCALED array returned by lse_for_bwd."""
     B, Sq, H, D = q.shape
     Sk = k.shape[1]
     if scales is not None:   # (sq, sk, sv, sdo)
@@ -206,6 +214,7 @@ class CudaOps:
     """The injected step functions of ring_exec: thin calls into liblwm_b200.so."""
     fwd_step = staticmethod(fwd_step)
     bwd_prep = staticmethod(bwd_prep)
+    lse_for_bwd = staticmethod(lse_for_bwd)
     bwd_step = staticmethod(bwd_step)
     cast = staticmethod(cast_f32_to_bf16)
 
@@ -283,6 +292,7 @@ def ring_backward(res, k, v, dout, bias, seg, causal, group, rank, world, layout
         Sq = q.shape[1]
         delta = torch.empty((B, H, Sq), dtype=torch.float32, device=dev)
         bwd_prep(out, dout, delta)
+        lse = lse_for_bwd(lse)
         dq_acc = torch.zeros((B, Sq, H, D), dtype=torch.float32, device=dev)
         dk_acc = torch.zeros((B, Sk, H, D), dtype=torch.float32, device=dev)
         dv_acc = torch.zeros((B, Sk, H, D), dtype=torch.float32, device=dev)

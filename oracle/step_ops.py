@@ -61,6 +61,10 @@ class CpuOps:
         delta.copy_((out.double() * dout.double()).sum(-1).transpose(1, 2).to(delta.dtype))
 
     @staticmethod
+    def lse_for_bwd(lse):
+        return lse            # the CPU stand-in keeps the natural-log lse
+
+    @staticmethod
     def bwd_step(q, k, v, dout, lse, delta, dq_acc, dk_acc, dv_acc, q_pos0, k_pos0, causal, bias, seg):
         D = q.shape[-1]
         t = _logits2(q, k, q_pos0, k_pos0, causal, bias, seg)

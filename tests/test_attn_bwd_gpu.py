@@ -28,7 +28,7 @@ def _run_bwd(q, k, v, do, causal=True, q_pos0=0, k_pos0=0, bias=None, seg=None):
     dq = torch.zeros(B, Sq, H, D, dtype=torch.float32, device="cuda")
     dk = torch.zeros(B, Sk, H, D, dtype=torch.float32, device="cuda")
     dv = torch.zeros(B, Sk, H, D, dtype=torch.float32, device="cuda")
-    ra.bwd_step(q, k, v, do, lse, delta, dq, dk, dv, q_pos0, k_pos0, causal, bias, seg)
+    ra.bwd_step(q, k, v, do, ra.lse_for_bwd(lse), delta, dq, dk, dv, q_pos0, k_pos0, causal, bias, seg)
     torch.cuda.synchronize()
     return out, lse, delta, dq, dk, dv
 

@@ -34,7 +34,8 @@ def main():
             dk = torch.zeros_like(dq)
             dv = torch.zeros_like(dq)
             ra.bwd_prep(out, do, delta)
-            ms = time_fn(lambda: ra.bwd_step(q, k, v, do, lse, delta, dq, dk, dv, 0, 0, True, None, None))
+            nl = ra.lse_for_bwd(lse)
+            ms = time_fn(lambda: ra.bwd_step(q, k, v, do, nl, delta, dq, dk, dv, 0, 0, True, None, None))
             print("bwd  causal S=%6d: %8.3f ms  %7.1f TFLOP/s" % (S, ms, 2.5 * f_fwd / ms / 1e9))
 
 

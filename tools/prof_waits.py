@@ -17,7 +17,7 @@ for _ in range(2):
 delta = torch.empty_like(lse); ra.bwd_prep(out, do, delta)
 dq = torch.zeros(B, S, H, D, dtype=torch.float32, device="cuda"); dk = torch.zeros_like(dq); dv = torch.zeros_like(dq)
 for _ in range(2):
-    ra.bwd_step(q, k, v, do, lse, delta, dq, dk, dv, 0, 0, True, None, None)
+    ra.bwd_step(q, k, v, do, ra.lse_for_bwd(lse), delta, dq, dk, dv, 0, 0, True, None, None)
 torch.cuda.synchronize()
 b = buf.cpu().tolist()
 n_it = S // 128
