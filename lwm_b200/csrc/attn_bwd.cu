@@ -28,6 +28,7 @@
 #include "attn_common.cuh"
 #include "tmap.h"
 #include "capi_internal.h"
+#include <type_traits>
 
 namespace lwm {
 
@@ -241,9 +242,6 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       const int q_tile_row0 = (i_start + it) * kTile;
       wp.wait(&bars.dq_full, it & 1, 0);
       tc_fence_after();
-      // previous iteration's TMA reduces have long finished reading the staging buffers
-      if (is_issuer) tma_wait_group_read<0>();
-      named_bar_sync(3, 128);
       auto stage_out = [&](const uint32_t (&a0)[32], const uint32_t (&a1)[32]) {
 #pragma unroll
         for (int c16 = 0; c16 < 8; ++c16) {
@@ -270,6 +268,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       };
       {
         uint32_t a0[32], a1[32];
+        const long long td0 = wp.on ? clock64() : 0;
         tmem_ld_x32(tR1, a0);
         tmem_ld_x32(tR1 + 32, a1);
         tmem_wait_ld();
@@ -279,15 +278,27 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         tmem_wait_ld();
         tc_fence_before();
         mbar_arrive(&bars.dq_drained);   // every lane of dQ has been read: R1 is free for the next dP^T
+        if (wp.on) wp.acc[1] += clock64() - td0;
         reduce_out(0);
+        const long long td1 = wp.on ? clock64() : 0;
         if (is_issuer) tma_wait_group_read<0>();
         named_bar_sync(3, 128);
+        if (wp.on) wp.acc[2] += clock64() - td1;
         stage_out(a0, a1);
         reduce_out(1);
+        // free the staging buffers now (this warpgroup idles until the next dQ anyway), so that the next drain can
+        // start its TMEM loads the moment dq_full fires
+        const long long td2 = wp.on ? clock64() : 0;
+        if (is_issuer) tma_wait_group_read<0>();
+        named_bar_sync(3, 128);
+        if (wp.on) wp.acc[3] += clock64() - td2;
       }
     }
     if (is_issuer) tma_wait_group<0>();
-    wp.flush(16, 1, clock64() - t_start);
+    if (wp.on) {   // prof slots 16: wait dq_full, 17: ld+stage until drained, 18/19: TMA-read waits, 22: total
+      for (int i = 0; i < 4; ++i) wp.buf[16 + i] = (unsigned long long)wp.acc[i];
+      wp.buf[22] = (unsigned long long)(clock64() - t_start);
+    }
   } else {
     // ------------------------------------------------------------------ compute warpgroups
     setmaxnreg_inc<192>();
@@ -319,15 +330,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
     // A) P^T = exp2(S^T * scale_log2 (+bias) - lse2) for Q tile `it`; bf16 P^T overwrites this
     //    warpgroup's half of S^T in TMEM (32 packed columns).
-    auto phase_a = [&](int it) {
+    // Two compiled versions (mask / no mask): written as one loop with an inner `if (need_mask)` the compiler
+    // if-converts the mask code into ~10 predicated-off instructions per element that still issue.
+    const int k_pos_i = int(k_pos);
+    auto phase_a_impl = [&](int it, auto mask_tag) {
+      constexpr bool kMask = decltype(mask_tag)::value;
       const int st = it & 1;
-      const long long q_tile_pos = (long long)p.mask.q_pos0 + (long long)(i_start + it) * kTile;
-      const bool need_mask = has_bias || has_seg ||
-                             (p.mask.causal && (q_tile_pos < (long long)p.mask.k_pos0 + (long long)n * kTile + kTile - 1));
-      wp.wait(&bars.q_full[st], (it >> 1) & 1, 0);  // lse / delta of this Q tile are in smem
-      wp.wait(&bars.s_full, it & 1, 1);
-      tc_fence_after();
-      const long long tA0 = wp.on ? clock64() : 0;
+      const int q_tile_pos = p.mask.q_pos0 + (i_start + it) * kTile;
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {
         uint32_t s[32];
@@ -339,23 +348,34 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #pragma unroll
         for (int c4 = 0; c4 < 8; ++c4) {
           const float4 l4 = lse4[c4];
-          const float ls[4] = {l4.x, l4.y, l4.z, l4.w};
+          const float ls[4] = {l4.x, l4.y, l4.z, l4.w};   // -lse*log2e (or -inf): lwm_attn_bwd_lse
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const int c = c4 * 4 + e;
-            // ls = -lse*log2e, or -inf for rows at the masked level (p = 0, no gradient): lwm_attn_bwd_lse
-            const float nl2 = ls[e];
-            float tv = __uint_as_float(s[c]) * scale_log2;
-            if (need_mask) {
-              tv = key_masked ? kMaskedLogit : tv + bias_t;
-              const long long q_pos = q_tile_pos + wg * 64 + hh * 32 + c;
+            if (!kMask) {
+              pr[hh * 32 + c] = ex2f(fmaf(__uint_as_float(s[c]), scale_log2, ls[e]));
+            } else {
+              float tv = key_masked ? kMaskedLogit : fmaf(__uint_as_float(s[c]), scale_log2, bias_t);
+              const int q_pos = q_tile_pos + wg * 64 + hh * 32 + c;
               if (has_seg && seg_row[q_pos] != my_seg) tv = kMaskedLogit;
-              if (p.mask.causal && q_pos < k_pos) tv = kMaskedLogit;
+              if (p.mask.causal && q_pos < k_pos_i) tv = kMaskedLogit;
+              pr[hh * 32 + c] = ex2f(tv + ls[e]);
             }
-            pr[hh * 32 + c] = ex2f(tv + nl2);
           }
         }
       }
+    };
+    auto phase_a = [&](int it) {
+      const int st = it & 1;
+      const long long q_tile_pos = (long long)p.mask.q_pos0 + (long long)(i_start + it) * kTile;
+      const bool need_mask = has_bias || has_seg ||
+                             (p.mask.causal && (q_tile_pos < (long long)p.mask.k_pos0 + (long long)n * kTile + kTile - 1));
+      wp.wait(&bars.q_full[st], (it >> 1) & 1, 0);  // lse / delta of this Q tile are in smem
+      wp.wait(&bars.s_full, it & 1, 1);
+      tc_fence_after();
+      const long long tA0 = wp.on ? clock64() : 0;
+      if (need_mask) phase_a_impl(it, std::true_type{});
+      else phase_a_impl(it, std::false_type{});
       // all 64 logits of this half have been read: the packed P^T may overwrite columns [0,32)
       uint32_t pk[32];
 #pragma unroll
@@ -365,6 +385,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       tmem_wait_st();
       tc_fence_before();
       mbar_arrive(&bars.p_ready);
+      // fold the softmax scale (and the fp16 boost) into P now: this phase runs in the shadow of the dQ/dK
+      // UMMAs, phase B (dS) is on the critical dP^T -> dS -> dQ -> drain loop
+#pragma unroll
+      for (int i = 0; i < 64; ++i) pr[i] *= ds_mul;
       if (wp.on) {
         wp.acc[4] += clock64() - ts0;
         wp.acc[5] += clock64() - tA0;
@@ -374,6 +398,17 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     // B) dS^T = P^T o (dP^T - delta) * scale  -> smem (bf16, 128B-swizzled K-major tile)
     auto phase_b = [&](int it) {
       const int st = it & 1;
+      // delta of this Q tile -> registers BEFORE the dS stores: the compiler cannot hoist shared-memory loads
+      // above the st.shared of the previous 8 elements (possible aliasing), which serialised load->math->store
+      float dl[64];
+      {
+        const float4* dl4 = reinterpret_cast<const float4*>(&s_delta[st][wg * 64]);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float4 d4 = dl4[i];
+          dl[4 * i] = d4.x; dl[4 * i + 1] = d4.y; dl[4 * i + 2] = d4.z; dl[4 * i + 3] = d4.w;
+        }
+      }
       wp.wait(&bars.dp_full, it & 1, 2);
       tc_fence_after();
       const long long tB0 = wp.on ? clock64() : 0;
@@ -384,19 +419,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         tmem_ld_x32(tR1 + hh * 32, d);
         tmem_wait_ld();
         if (wp.on) wp.acc[6] += clock64() - tl0;
-        const float4* dl4 = reinterpret_cast<const float4*>(&s_delta[st][wg * 64 + hh * 32]);
 #pragma unroll
-        for (int c16 = 0; c16 < 4; ++c16) {  // 8 bf16 (16 B) per store
+        for (int c16 = 0; c16 < 4; ++c16) {  // 8 elements (16 B of bf16/fp16) per store
           float dsv[8];
 #pragma unroll
-          for (int h2 = 0; h2 < 2; ++h2) {
-            const float4 d4 = dl4[c16 * 2 + h2];
-            const float dl[4] = {d4.x, d4.y, d4.z, d4.w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int c = c16 * 8 + h2 * 4 + e;
-              dsv[h2 * 4 + e] = pr[hh * 32 + c] * (__uint_as_float(d[c]) * dp_mul - dl[e]) * ds_mul;
-            }
+          for (int e = 0; e < 8; ++e) {
+            const int c = hh * 32 + c16 * 8 + e;
+            dsv[e] = pr[c] * fmaf(__uint_as_float(d[c16 * 8 + e]), dp_mul, -dl[c]);   // pr already carries ds_mul
           }
           const uint4 v4 = kF16 ? make_uint4(pack_f16x2(dsv[0], dsv[1]), pack_f16x2(dsv[2], dsv[3]),
                                              pack_f16x2(dsv[4], dsv[5]), pack_f16x2(dsv[6], dsv[7]))
@@ -410,10 +439,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       if (wp.on) wp.acc[7] += clock64() - tB0;
     };
 
-    phase_a(0);
-    for (int it = 0; it < nq; ++it) {
-      phase_b(it);
-      if (it + 1 < nq) phase_a(it + 1);   // overlaps the dK(it), dQ(it) UMMAs
+    // order: A(0) B(0) A(1) B(1) ... — A(it+1) overlaps the dQ(it), dK(it) UMMAs. One call site per phase keeps
+    // the unrolled code (and the L0 I-cache footprint) small.
+    for (int it = 0; it <= nq; ++it) {
+      if (it > 0) phase_b(it - 1);
+      if (it < nq) phase_a(it);
     }
     // prof slots 8..10 waits (q_full, s_full, dp_full); 11,12: A tmem-ld, A st+arrive; 13: A total; 14: B tmem-ld; 15: B total
     if (wp.on) {

@@ -31,7 +31,8 @@ tot = b[20]
 print(" compute thread0 total %d = %.0f/iter; waits q_full %.0f s_full %.0f dp_full %.0f per iter" % (tot, tot / n_it, b[8] / n_it, b[9] / n_it, b[10] / n_it))
 print("   phase A (exp) %.0f/iter of which tmem-ld+wait %.0f, pack+tmem-st+arrive %.0f ; phase B (dS) %.0f/iter of which tmem-ld+wait %.0f" % (
     b[13] / n_it, b[11] / n_it, b[12] / n_it, b[15] / n_it, b[14] / n_it))
-print(" drain issuer total %d = %.0f/iter; wait dq_full %.0f/iter" % (b[17], b[17] / n_it, b[16] / n_it))
+print(" drain issuer total %d = %.0f/iter; wait dq_full %.0f, ld+stage->drained %.0f, TMA-read wait #1 %.0f, #2 %.0f per iter" % (
+    b[22], b[22] / n_it, b[16] / n_it, b[17] / n_it, b[18] / n_it, b[19] / n_it))
 # fwd: CTA (0,0,0) = last q pair => n_kv = S/128 tiles
 tot = b[36]
 print("fwd CTA(0,0,0): MMA issuer total %d = %.0f cyc/kv-tile" % (tot, tot / n_it))
