@@ -299,8 +299,14 @@ def main():
         del dq, dk, dv
         fl_bwd = 2.5 * f_fwd(S)
         ach = fl_bwd / (kern_ms["bwd"] * 1e-3) / 1e12
+        traffic = None   # dram__bytes_read+write of one attn_bwd_kernel launch at S=131072 (ncu --set full capture)
+        tp = os.path.join(ROOT, "profiles", "ncu_attn_128k_r01.json")
+        if S == S_TOTAL and os.path.exists(tp):
+            traffic = json.load(open(tp))["attn_bwd_kernel"]["dram_total_bytes"]
         roof = {"bound": "tensor", "kernel": "attn_bwd_kernel", "achieved": ach, "peak": peaks["sustained"],
-                "unit": "TFLOP/s", "frac": ach / peaks["sustained"], "traffic": None,
+                "unit": "TFLOP/s", "frac": ach / peaks["sustained"], "traffic": traffic,
+                "traffic_note": "bytes per launch from profiles/ncu_attn_128k_r01.json; algorithmic minimum ~17 GB "
+                                "(q,k,v,dout once + dq/dk/dv fp32 read-modify-write); tensor-bound, HBM < 2 % busy",
                 "peak_source": peaks["source"] + " bf16_tflops_sustained (kernel timed inside a long step); burst=%.1f"
                 % peaks["burst"],
                 "fwd_kernel": {"achieved": f_fwd(S) / (kern_ms["fwd"] * 1e-3) / 1e12,
