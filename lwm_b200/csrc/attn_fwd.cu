@@ -40,6 +40,13 @@ struct FwdParams {
 };
 
 constexpr int kFwdStages = 4;
+// Measured (round 1): routing every 4th exp2 through the FMA-pipe polynomial (ex2_poly3) does NOT pay off here —
+// 965 vs 1026 TFLOP/s at S=131072 — the ~10 extra instructions per element make the softmax warps issue-bound
+// before the XU pipe is relieved. Kept as an opt-in (-DLWM_FWD_POLY_EXP=1) for the 64-wide-S-tile redesign.
+#ifndef LWM_FWD_POLY_EXP
+#define LWM_FWD_POLY_EXP 0
+#endif
+constexpr bool kPolyExp = LWM_FWD_POLY_EXP != 0;
 constexpr int kFwdTileBytes = kTile * kHeadDim * 2;  // 32 KB
 constexpr int kFwdThreads = 384;  // 2 softmax warpgroups + 1 producer warpgroup (TMA, UMMA, 2 idle warps)
 constexpr int kFwdSmemBytes = (2 + kFwdStages) * kFwdTileBytes + 1024;
@@ -298,7 +305,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
               e0 = ex2f(fmaf(__uint_as_float(s[c][i + 0]), scale, neg_m));
               e1 = ex2f(fmaf(__uint_as_float(s[c][i + 1]), scale, neg_m));
               e2 = ex2f(fmaf(__uint_as_float(s[c][i + 2]), scale, neg_m));
-              e3 = ex2f(fmaf(__uint_as_float(s[c][i + 3]), scale, neg_m));
+              e3 = kPolyExp ? ex2_poly3(fmaf(__uint_as_float(s[c][i + 3]), scale, neg_m))
+                            : ex2f(fmaf(__uint_as_float(s[c][i + 3]), scale, neg_m));
             } else {
               e0 = ex2f(__uint_as_float(s[c][i + 0]) + neg_m);
               e1 = ex2f(__uint_as_float(s[c][i + 1]) + neg_m);

@@ -260,6 +260,19 @@ LWM_DEVICE float ex2f(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// 2^x on the FMA/ALU pipes (no MUFU): round-to-nearest split x = n + f, f in [-0.5, 0.5], degree-3 polynomial
+// for 2^f (max relative error 1.03e-4, below the bf16/fp16 rounding of P), exponent patched in by integer add.
+// The forward softmax is bound by the 16-lane/clk XU pipe (ncu: XU 51 % busy while the tensor pipe is 51 %);
+// routing a quarter of the exponentials here balances XU against the issue slots.
+LWM_DEVICE float ex2_poly3(float x) {
+  x = fmaxf(x, -126.0f);
+  const float xr = x + 12582912.0f;
+  const float f = x - (xr - 12582912.0f);
+  float p = fmaf(f, 0.05592203565f, 0.24264008283f);
+  p = fmaf(f, p, 0.69312103399f);
+  p = fmaf(f, p, 0.99992448146f);
+  return __int_as_float(__float_as_int(p) + ((__float_as_int(xr) - 0x4B400000) << 23));
+}
 template <int kRegs>
 LWM_DEVICE void setmaxnreg_inc() {
   asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegs));

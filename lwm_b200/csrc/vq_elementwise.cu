@@ -99,40 +99,59 @@ __global__ void prep_kernel(const float* __restrict__ x, const double* __restric
 }
 
 // ------------------------------------------------------------------------------------------------
-// direct conv, Cin = 3, 3x3 SAME, Cout multiple of 32: block = 8x8 output pixels x all Cout,
-// weights [27][Cout] in smem, each thread = one pixel x 32 output channels.
+// direct conv, Cin = 3, 3x3 SAME, Cout = 128: block = 8 rows x 16 cols of output pixels x all 128 channels,
+// 128 threads; thread = 8 consecutive pixels of one row x 16 output channels (a 128-register tile: 12 shared-
+// memory loads feed 128 FMAs per tap — the first version did one load per FMA and was LSU-bound at 1.8 ms).
 // ------------------------------------------------------------------------------------------------
-__global__ void conv_cin3_kernel(const float* __restrict__ x, const float* __restrict__ w,
-                                 const float* __restrict__ bias, float* __restrict__ y, int N, int H, int W,
-                                 int Cout) {
-  extern __shared__ float s_w[];  // [27][Cout] then input patch [10][10][3]
-  float* s_in = s_w + 27 * Cout;
-  const int tiles_w = W / 8;
+__global__ void __launch_bounds__(128)
+conv_cin3_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                 float* __restrict__ y, int N, int H, int W) {
+  constexpr int Cout = 128;
+  __shared__ __align__(16) float s_w[27 * Cout];   // HWIO order: [(kh*3+kw)*3+c][cout]
+  __shared__ float s_in[10 * 18 * 3];               // input patch with a 1-pixel halo
+  const int tiles_w = W / 16;
   const int tw = blockIdx.x % tiles_w, th = blockIdx.x / tiles_w, n = blockIdx.y;
-  for (int i = threadIdx.x; i < 27 * Cout; i += blockDim.x) s_w[i] = w[i];
-  for (int i = threadIdx.x; i < 300; i += blockDim.x) {
-    const int c = i % 3, px = (i / 3) % 10, py = i / 30;
-    const int gy = th * 8 + py - 1, gx = tw * 8 + px - 1;
+  for (int i = threadIdx.x; i < 27 * Cout / 4; i += blockDim.x)
+    reinterpret_cast<float4*>(s_w)[i] = reinterpret_cast<const float4*>(w)[i];
+  for (int i = threadIdx.x; i < 10 * 18 * 3; i += blockDim.x) {
+    const int c = i % 3, px = (i / 3) % 18, py = i / 54;
+    const int gy = th * 8 + py - 1, gx = tw * 16 + px - 1;
     s_in[i] = (gy >= 0 && gy < H && gx >= 0 && gx < W) ? x[(((size_t)n * H + gy) * W + gx) * 3 + c] : 0.f;
   }
   __syncthreads();
-  const int groups_c = Cout / 32;
-  const int pix = threadIdx.x / groups_c, cg = threadIdx.x % groups_c;  // blockDim = 64 * groups_c
-  const int py = pix / 8, px = pix % 8;
-  float acc[32];
+  const int cg = threadIdx.x & 7;        // 16 output channels [16*cg, 16*cg+16)
+  const int pg = threadIdx.x >> 3;       // 16 pixel groups: row pg>>1, columns 8*(pg&1) .. +8
+  const int row = pg >> 1, x0 = (pg & 1) * 8;
+  float acc[8][16];
 #pragma unroll
-  for (int j = 0; j < 32; ++j) acc[j] = bias[cg * 32 + j];
+  for (int j = 0; j < 16; ++j) {
+    const float b = bias[cg * 16 + j];
+#pragma unroll
+    for (int p2 = 0; p2 < 8; ++p2) acc[p2][j] = b;
+  }
 #pragma unroll
   for (int t = 0; t < 27; ++t) {
-    const int kh = t / 9, kw = (t / 3) % 3, c = t % 3;   // HWIO order: (kh, kw, cin)
-    const float a = s_in[((py + kh) * 10 + (px + kw)) * 3 + c];
-    const float* wr = s_w + t * Cout + cg * 32;
+    const int kh = t / 9, kw = (t / 3) % 3, c = t % 3;
+    float a[8], wv[16];
 #pragma unroll
-    for (int j = 0; j < 32; ++j) acc[j] = fmaf(a, wr[j], acc[j]);
+    for (int p2 = 0; p2 < 8; ++p2) a[p2] = s_in[((row + kh) * 18 + (x0 + p2 + kw)) * 3 + c];
+#pragma unroll
+    for (int j4 = 0; j4 < 4; ++j4) {
+      const float4 w4 = *reinterpret_cast<const float4*>(&s_w[t * Cout + cg * 16 + 4 * j4]);
+      wv[4 * j4] = w4.x; wv[4 * j4 + 1] = w4.y; wv[4 * j4 + 2] = w4.z; wv[4 * j4 + 3] = w4.w;
+    }
+#pragma unroll
+    for (int p2 = 0; p2 < 8; ++p2)
+#pragma unroll
+      for (int j = 0; j < 16; ++j) acc[p2][j] = fmaf(a[p2], wv[j], acc[p2][j]);
   }
-  float* dst = y + (((size_t)n * H + th * 8 + py) * W + tw * 8 + px) * Cout + cg * 32;
 #pragma unroll
-  for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+  for (int p2 = 0; p2 < 8; ++p2) {
+    float* dst = y + (((size_t)n * H + th * 8 + row) * W + tw * 16 + x0 + p2) * Cout + cg * 16;
+#pragma unroll
+    for (int j = 0; j < 16; j += 4)
+      *reinterpret_cast<float4*>(dst + j) = make_float4(acc[p2][j], acc[p2][j + 1], acc[p2][j + 2], acc[p2][j + 3]);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -296,11 +315,10 @@ extern "C" int lwm_vq_conv_cin3(const float* x, const float* w_hwio, const float
                                 int Cout, void* stream) {
   if (!lwm_check_device()) return LWM_ERR_DEVICE;
   if (!x || !w_hwio || !bias || !y) return lwm_fail(LWM_ERR_ARG, "vq_conv_cin3: null pointer");
-  if (H % 8 || W % 8 || Cout % 32 || Cout > 512) return lwm_fail(LWM_ERR_SHAPE, "vq_conv_cin3: H,W % 8, Cout % 32");
-  dim3 grid((H / 8) * (W / 8), N);
-  const int threads = 64 * (Cout / 32);
-  const size_t smem = (27 * Cout + 300) * sizeof(float);
-  conv_cin3_kernel<<<grid, threads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(x, w_hwio, bias, y, N, H, W, Cout);
+  if (H % 8 || W % 16 || Cout != 128)
+    return lwm_fail(LWM_ERR_SHAPE, "vq_conv_cin3: H % 8, W % 16 and Cout == 128 (hidden_channels, vqgan.py:64)");
+  dim3 grid((H / 8) * (W / 16), N);
+  conv_cin3_kernel<<<grid, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, w_hwio, bias, y, N, H, W);
   return lwm_check_launch("conv_cin3_kernel");
 }
 
