@@ -55,46 +55,57 @@ __global__ void prep_kernel(const float* __restrict__ x, const double* __restric
                             const float* __restrict__ gamma, const float* __restrict__ beta,
                             __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int N, int H, int W,
                             int C, int C_pad, int groups, int up, float eps, int write_lo) {
+  // one thread = 8 channels of one output pixel: 2 x 16 B loads, 16 B stores per plane
   const int Ho = H << up, Wo = W << up;
-  const int quads = C_pad / 4;
-  const size_t total = (size_t)N * Ho * Wo * quads;
+  const int octs = C_pad / 8;
+  const size_t total = (size_t)N * Ho * Wo * octs;
   const int cpg = C / groups;
   const double inv_cnt = 1.0 / ((double)H * W * cpg);
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int q = int(i % quads);
-    size_t pix = i / quads;
+    const int o8 = int(i % octs);
+    size_t pix = i / octs;
     const int wo = int(pix % Wo);
     pix /= Wo;
     const int ho = int(pix % Ho);
     const int n = int(pix / Ho);
-    const int c = q * 4;
-    float y[4] = {0.f, 0.f, 0.f, 0.f};
-    if (c < C) {
-      const float4 v = *reinterpret_cast<const float4*>(x + (((size_t)n * H + (ho >> up)) * W + (wo >> up)) * C + c);
-      y[0] = v.x; y[1] = v.y; y[2] = v.z; y[3] = v.w;
-      if (stats) {
-        const int g = c / cpg;
-        const double sum = stats[((size_t)n * groups + g) * 2], sumsq = stats[((size_t)n * groups + g) * 2 + 1];
-        const float mean = float(sum * inv_cnt);
-        float var = float(sumsq * inv_cnt) - mean * mean;   // flax fast variance, clamped at 0
-        var = fmaxf(var, 0.f);
-        const float rstd = rsqrtf(var + eps);
+    const int c0 = o8 * 8;
+    float y[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const float* src = x + (((size_t)n * H + (ho >> up)) * W + (wo >> up)) * C + c0;
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float t = (y[e] - mean) * rstd * gamma[c + e] + beta[c + e];
-          y[e] = t / (1.0f + __expf(-t));   // silu = t * sigmoid(t)
+    for (int hq = 0; hq < 2; ++hq) {
+      const int c = c0 + hq * 4;
+      if (c < C) {
+        const float4 v = *reinterpret_cast<const float4*>(src + hq * 4);
+        float* yy = y + hq * 4;
+        yy[0] = v.x; yy[1] = v.y; yy[2] = v.z; yy[3] = v.w;
+        if (stats) {
+          const int g = c / cpg;
+          const double sum = stats[((size_t)n * groups + g) * 2], sumsq = stats[((size_t)n * groups + g) * 2 + 1];
+          const float mean = float(sum * inv_cnt);
+          float var = float(sumsq * inv_cnt) - mean * mean;   // flax fast variance, clamped at 0
+          var = fmaxf(var, 0.f);
+          const float rstd = rsqrtf(var + eps);
+          const float4 g4 = *reinterpret_cast<const float4*>(gamma + c);
+          const float4 b4 = *reinterpret_cast<const float4*>(beta + c);
+          const float gg[4] = {g4.x, g4.y, g4.z, g4.w}, bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float t = (yy[e] - mean) * rstd * gg[e] + bb[e];
+            yy[e] = t / (1.0f + __expf(-t));   // silu = t * sigmoid(t)
+          }
         }
       }
     }
-    __nv_bfloat16 h4[4], l4[4];
+    uint32_t h4[4], l4[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      h4[e] = __float2bfloat16_rn(y[e]);
-      l4[e] = __float2bfloat16_rn(y[e] - __bfloat162float(h4[e]));
+      const __nv_bfloat16 h0 = __float2bfloat16_rn(y[2 * e]), h1 = __float2bfloat16_rn(y[2 * e + 1]);
+      h4[e] = uint32_t(__bfloat16_as_ushort(h0)) | (uint32_t(__bfloat16_as_ushort(h1)) << 16);
+      l4[e] = pack_bf16x2(y[2 * e] - __bfloat162float(h0), y[2 * e + 1] - __bfloat162float(h1));
     }
-    const size_t o = (((size_t)n * Ho + ho) * Wo + wo) * C_pad + c;
-    *reinterpret_cast<uint2*>(hi + o) = *reinterpret_cast<const uint2*>(h4);
-    if (write_lo) *reinterpret_cast<uint2*>(lo + o) = *reinterpret_cast<const uint2*>(l4);
+    const size_t o = (((size_t)n * Ho + ho) * Wo + wo) * C_pad + c0;
+    *reinterpret_cast<uint4*>(hi + o) = make_uint4(h4[0], h4[1], h4[2], h4[3]);
+    if (write_lo) *reinterpret_cast<uint4*>(lo + o) = make_uint4(l4[0], l4[1], l4[2], l4[3]);
   }
 }
 
@@ -298,10 +309,10 @@ extern "C" int lwm_vq_prep(const float* x, const double* gn_stats, const float* 
                            void* stream) {
   if (!lwm_check_device()) return LWM_ERR_DEVICE;
   if (!x || !hi) return lwm_fail(LWM_ERR_ARG, "vq_prep: null pointer");
-  if (C % 4 || C_pad % 4 || C_pad < C) return lwm_fail(LWM_ERR_SHAPE, "vq_prep: C and C_pad must be multiples of 4");
+  if (C % 4 || C_pad % 8 || C_pad < C) return lwm_fail(LWM_ERR_SHAPE, "vq_prep: C % 4 and C_pad % 8 required");
   if (gn_stats && (!gamma || !beta || C % groups || (C / groups) % 4))
     return lwm_fail(LWM_ERR_SHAPE, "vq_prep: GroupNorm needs gamma/beta and C/groups % 4 == 0");
-  const size_t total = (size_t)N * (H << upsample2x) * (W << upsample2x) * (C_pad / 4);
+  const size_t total = (size_t)N * (H << upsample2x) * (W << upsample2x) * (C_pad / 8);
   const int threads = 256;
   const size_t want = (total + threads - 1) / threads;
   const unsigned blocks = unsigned(want < 148u * 32 ? want : 148u * 32);

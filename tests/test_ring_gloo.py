@@ -16,7 +16,7 @@ import torch.multiprocessing as mp
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _worker(rank, world, port, layout, use_masks, ret, n_sub=1):
+def _worker(rank, world, port, layout, use_masks, ret, n_sub=1, batch=1):
     sys.path.insert(0, ROOT)
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -26,7 +26,7 @@ def _worker(rank, world, port, layout, use_masks, ret, n_sub=1):
         from oracle.step_ops import CpuOps
         from oracle.attn_dense import attention_dense, attention_dense_grads, finfo_min
         torch.manual_seed(0)
-        B, S, H, D = 1, 256 * world * n_sub, 2, 16   # zigzag half-chunks of 128 * n_sub rows
+        B, S, H, D = batch, 256 * world * n_sub, 2, 16   # zigzag half-chunks of 128 * n_sub rows
         Sl = S // world
         g = torch.Generator().manual_seed(42)
         q, k, v, do = [torch.randn(B, S, H, D, generator=g) for _ in range(4)]
@@ -81,6 +81,15 @@ def test_ring_schedules_match_dense_oracle(world, layout, use_masks):
     mp.spawn(_worker, args=(world, _free_port(), layout, use_masks, ret), nprocs=world, join=True)
     assert len(ret) == world
     for r in range(world):
+        for e in ret[r]:
+            assert e < 1e-5, (r, ret[r])
+
+
+def test_ring_batch_gt_one_matches_dense_oracle():
+    """B > 1: sequence slices of [B,S,H,D] are no longer contiguous views (staged copies in ring_exec)"""
+    ret = mp.Manager().dict()
+    mp.spawn(_worker, args=(2, _free_port(), "zigzag", True, ret, 1, 2), nprocs=2, join=True)
+    for r in range(2):
         for e in ret[r]:
             assert e < 1e-5, (r, ret[r])
 
