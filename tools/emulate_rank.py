@@ -14,7 +14,7 @@ B, H, D = 1, 32, 128
 
 
 class FakeComm(rx._Comm):
-    def __init__(self, group, device):
+    def __init__(self, group, device, channel=0):
         self.group, self.device, self.cuda, self.stream = group, device, False, None
 
     def exchange(self, sends, recvs, after_event=None):
