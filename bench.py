@@ -158,9 +158,8 @@ def bench_vqgan(dev, peaks, world):
     """VQGAN encode of a 16-frame 256x256 clip (BASELINE 'VQGAN frames/s'), synthetic weights and pixels.
     Byte accounting = SURVEY.md §8d minimum-traffic model with fp32 activations: 815.5 MB / frame."""
     import torch
-    from lwm_b200.vqgan import VQGAN
-    from oracle import vqgan_ref   # only to draw random parameters with the reference's shapes
-    params = vqgan_ref.init_params(seed=0, codebook="normal")
+    from lwm_b200.vqgan import VQGAN, init_params
+    params = init_params(seed=0, codebook="normal")
     g = torch.Generator().manual_seed(1234)
     x = (torch.rand(16, 256, 256, 3, generator=g) * 2 - 1).to(dev)
     out = {}

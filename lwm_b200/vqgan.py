@@ -54,6 +54,60 @@ class VQGANConfig:
         return cls(**(updates or {}))
 
 
+def init_params(config=None, seed=0, codebook="normal"):
+    """Random parameters in the flax tree layout of lwm/vqgan.py (for synthetic benchmarks; real use loads the
+    pickled checkpoint). Conv kernels HWIO ~ N(0, 1/(k^2 Cin)), GroupNorm scale 1 / bias 0 perturbed by N(0, 0.02),
+    codebook N(0,1) or the reference initialiser U(-1/n_e, 1/n_e) (vqgan.py:198-200)."""
+    cfg = config or VQGANConfig.get_default_config()
+    g = torch.Generator().manual_seed(seed)
+
+    def conv(k, cin, cout):
+        return {"kernel": torch.randn(k, k, cin, cout, generator=g) * (1.0 / (k * k * cin) ** 0.5),
+                "bias": torch.randn(cout, generator=g) * 0.02}
+
+    def gn(c):
+        return {"scale": 1.0 + 0.02 * torch.randn(c, generator=g), "bias": 0.02 * torch.randn(c, generator=g)}
+
+    def resnet(cin, cout):
+        p = {"GroupNorm_0": gn(cin), "Conv_0": conv(3, cin, cout), "GroupNorm_1": gn(cout), "Conv_1": conv(3, cout, cout)}
+        if cin != cout:
+            p["Conv_2"] = conv(1, cin, cout)
+        return p
+
+    hc, mult, nres, nlev = cfg.hidden_channels, cfg.channel_mult, cfg.num_res_blocks, cfg.num_resolutions
+    enc = {"Conv_0": conv(3, cfg.num_channels, hc)}
+    cin = hc
+    for i in range(nlev):
+        blk = {}
+        for j in range(nres):
+            blk["ResnetBlock_%d" % j] = resnet(cin, hc * mult[i])
+            cin = hc * mult[i]
+        if i != nlev - 1:
+            blk["Downsample_0"] = {"Conv_0": conv(3, cin, cin)}
+        enc["DownsamplingBlock_%d" % i] = blk
+    enc["MidBlock_0"] = {"ResnetBlock_0": resnet(cin, cin), "ResnetBlock_1": resnet(cin, cin)}
+    enc["GroupNorm_0"] = gn(cin)
+    enc["Conv_1"] = conv(3, cin, cfg.z_channels)
+    ctop = hc * mult[-1]
+    dec = {"Conv_0": conv(3, cfg.z_channels, ctop),
+           "MidBlock_0": {"ResnetBlock_0": resnet(ctop, ctop), "ResnetBlock_1": resnet(ctop, ctop)}}
+    cin = ctop
+    for n, i in enumerate(reversed(range(nlev))):      # UpsamplingBlock_0 <=> block_idx nlev-1 (vqgan.py:179-180)
+        blk = {}
+        for j in range(nres + 1):
+            blk["ResnetBlock_%d" % j] = resnet(cin, hc * mult[i])
+            cin = hc * mult[i]
+        if i != 0:
+            blk["Upsample_0"] = {"Conv_0": conv(3, cin, cin)}
+        dec["UpsamplingBlock_%d" % n] = blk
+    dec["GroupNorm_0"] = gn(cin)
+    dec["Conv_1"] = conv(3, cin, cfg.num_channels)
+    n_e, e_dim = cfg.num_embeddings, cfg.quantized_embed_dim
+    emb = torch.randn(n_e, e_dim, generator=g) if codebook == "normal" else (torch.rand(n_e, e_dim, generator=g) * 2 - 1) / n_e
+    return {"encoder": enc, "decoder": dec, "quantize": {"embeddings": emb},
+            "quant_conv": conv(1, cfg.z_channels, e_dim), "post_quant_conv": conv(1, e_dim, cfg.z_channels)}
+
+
 def _pad_to(n, m):
     return (n + m - 1) // m * m
 

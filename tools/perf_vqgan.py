@@ -2,11 +2,10 @@
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from lwm_b200.vqgan import VQGAN
-from oracle import vqgan_ref
+from lwm_b200.vqgan import VQGAN, init_params
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 16
 prec = sys.argv[2] if len(sys.argv) > 2 else "bf16x3"
-params = vqgan_ref.init_params(seed=0)
+params = init_params(seed=0)
 x = (torch.rand(n, 256, 256, 3) * 2 - 1).cuda()
 tok = VQGAN(params, precision=prec)
 for _ in range(2):
