@@ -343,6 +343,10 @@ def ringattention_inference(q, k, v, attn_mask, axis_name="sp"):
     group, rank, world = _resolve_group(axis_name)
     B, Q, H, D = q.shape
     Sk = k.shape[1]
+    if world > 1 and Q != 1:
+        # the reference shards q along 'sp' when q_len > 1 (q_sp_dim, lwm/llama.py:598); that short-sequence
+        # prefill variant needs a q all-gather + per-row partial exchange and is not built (q_len == 1 decode is)
+        raise NotImplementedError("ringattention_inference across a ring supports q_len == 1 (decode) only")
     mask = None
     if attn_mask is not None:
         if attn_mask.dim() != 4 or attn_mask.shape[1] != 1 or attn_mask.shape[2] != Q:
