@@ -119,6 +119,18 @@ int lwm_attn_decode_partial(const void* q, const void* k, const void* v, const u
 int lwm_attn_decode_merge(const float* o_parts, const float* ml_parts, int n_part, void* out, float* lse,
                           long long rows, void* stream);
 
+/* Attention prologue: rotary position embedding (lwm/llama.py:344-375 precompute_freqs_cis / apply_rotary_emb, applied
+ * at llama.py:517-519 on the head-split projections right before the ring-attention call).
+ * xq [B,S,Hq,128], xk [B,S,Hk,128] (= the [B,S,H*128] projection outputs: the head split is a view), dtype codes
+ * 0 = fp32, 1 = bf16; out_* same shapes in out_dtype (the reference's `dtype` argument). position_ids [B,S] int32
+ * (global positions; llama.py:515 gathers the table by them); inv_freq [64] fp32 = 1/theta^(2j/128) as the table builder
+ * computes it (host mirror: lwm_b200.rope.precompute_inv_freq). The complex64 table is not materialised: the angle
+ * float32(float64(pos)*float64(inv_freq[j])) is rebuilt in-kernel, cos/sin correctly rounded from double.
+ * conj != 0 multiplies by the conjugate (the VJP of the rotation: gradients w.r.t. the un-rotated q/k). Hk may be 0. */
+int lwm_attn_rope(const void* xq, const void* xk, int in_dtype, void* out_q, void* out_k, int out_dtype,
+                  const int* position_ids, const float* inv_freq, int B, int S, int Hq, int Hk, int D, int conj,
+                  void* stream);
+
 /* Element-wise helpers used by the ring host loop. */
 int lwm_cast_f32_to_bf16(const float* src, void* dst, long long n, void* stream);
 /* dst[i] += src[i] (fp32, n % 4 == 0): folds a dK/dV partial received from a peer into the owner's accumulator. */
@@ -155,6 +167,15 @@ int lwm_vq_conv_cin3(const float* x, const float* w_hwio, const float* bias, flo
 int lwm_vq_argmin(const float* z, const float* codebook, int* idx, float* zq_st, void* workspace, int N, int n_e,
                   int e_dim, void* stream);
 int lwm_vq_gather(const int* idx, const float* codebook, float* out, long long N, int n_e, int e_dim, void* stream);
+
+/* Vision token framing. lwm_vq_frame_tokens: codes [n_clips, T_in, P] int32 -> tokens
+ * [n_clips, T_out, P+1]: every kept frame's P codes followed by eof_token, or eov_token after the clip's last frame
+ * (lwm/vision_chat.py:97-104; lwm/data.py:193-212, defaults P=256, eof=8192, eov=8193 at data.py:134-136).
+ * frame_idx [T_out] (device, or NULL when T_out == T_in) selects source frames (data.py:196-202 uniform selection).
+ * lwm_vq_unframe_tokens: tokens [n_frames, P+1] -> codes [n_frames, P] (lwm/vision_generation.py:160,221). */
+int lwm_vq_frame_tokens(const int* codes, const int* frame_idx, int* tokens, int n_clips, int T_in, int T_out,
+                        int tokens_per_frame, int eof_token, int eov_token, void* stream);
+int lwm_vq_unframe_tokens(const int* tokens, int* codes, long long n_frames, int tokens_per_frame, void* stream);
 
 /* Debug only: device buffer (>= 64 uint64) that the attention kernels fill with per-role barrier-wait cycle
  * counts of CTA (0,0,0) (tools/prof_waits.py); NULL disables. */

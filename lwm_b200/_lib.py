@@ -37,6 +37,9 @@ _SIGNATURES = {
     "lwm_vq_conv_cin3": [c_void_p] * 4 + [c_int] * 4 + [c_void_p],
     "lwm_vq_argmin": [c_void_p] * 5 + [c_int] * 3 + [c_void_p],
     "lwm_vq_gather": [c_void_p] * 3 + [c_ll, c_int, c_int, c_void_p],
+    "lwm_attn_rope": [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p] + [c_int] * 6 + [c_void_p],
+    "lwm_vq_frame_tokens": [c_void_p] * 3 + [c_int] * 6 + [c_void_p],
+    "lwm_vq_unframe_tokens": [c_void_p, c_void_p, c_ll, c_int, c_void_p],
 }
 
 
