@@ -20,24 +20,35 @@ constexpr int kRopeDim = 128;
 constexpr int kRopePairs = kRopeDim / 2;
 constexpr int kRopePos = 4;
 
+// 8 consecutive elements as loaded (kept raw until use, so that a batch of loads costs few registers)
 template <typename T>
-__device__ __forceinline__ void load8(const T* p, float (&x)[8]);
+struct Raw8;
 template <>
-__device__ __forceinline__ void load8<float>(const float* p, float (&x)[8]) {
-  const float4 a = reinterpret_cast<const float4*>(p)[0];
-  const float4 b = reinterpret_cast<const float4*>(p)[1];
-  x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
-}
-template <>
-__device__ __forceinline__ void load8<__nv_bfloat16>(const __nv_bfloat16* p, float (&x)[8]) {
-  const uint4 a = reinterpret_cast<const uint4*>(p)[0];
-  const unsigned w[4] = {a.x, a.y, a.z, a.w};
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    x[2 * i] = __uint_as_float(w[i] << 16);
-    x[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+struct Raw8<float> {
+  float4 a, b;
+  static constexpr int kBatch = 4;
+  __device__ __forceinline__ void load(const float* p) {
+    a = reinterpret_cast<const float4*>(p)[0];
+    b = reinterpret_cast<const float4*>(p)[1];
   }
-}
+  __device__ __forceinline__ void unpack(float (&x)[8]) const {
+    x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+  }
+};
+template <>
+struct Raw8<__nv_bfloat16> {
+  uint4 a;
+  static constexpr int kBatch = 8;
+  __device__ __forceinline__ void load(const __nv_bfloat16* p) { a = reinterpret_cast<const uint4*>(p)[0]; }
+  __device__ __forceinline__ void unpack(float (&x)[8]) const {
+    const unsigned w[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      x[2 * i] = __uint_as_float(w[i] << 16);
+      x[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    }
+  }
+};
 template <typename T>
 __device__ __forceinline__ void store8(T* p, const float (&y)[8]);
 template <>
@@ -58,7 +69,7 @@ __device__ __forceinline__ void store8<__nv_bfloat16>(__nv_bfloat16* p, const fl
 }
 
 template <typename TIn, typename TOut>
-__global__ void __launch_bounds__(256) rope_kernel(const TIn* __restrict__ xq, const TIn* __restrict__ xk,
+__global__ void __launch_bounds__(256, 3) rope_kernel(const TIn* __restrict__ xq, const TIn* __restrict__ xk,
                                                    TOut* __restrict__ oq, TOut* __restrict__ ok,
                                                    const int* __restrict__ position_ids,
                                                    const float* __restrict__ inv_freq, long long n_tok, int Hq,
@@ -77,12 +88,12 @@ __global__ void __launch_bounds__(256) rope_kernel(const TIn* __restrict__ xq, c
   }
   __syncthreads();
   const int vq = Hq * (kRopeDim / 8), vk = Hk * (kRopeDim / 8), vt = vq + vk;
-  // batches of 4 independent 16/32-byte loads per thread before the first use: ~64 KB in flight per SM
-  constexpr int kBatch = 4;
+  // batches of independent 16/32-byte loads per thread (8 / 4) before the first use: ~100 KB in flight per SM
+  constexpr int kBatch = Raw8<TIn>::kBatch;
   const int total = kRopePos * vt;
   for (int base = threadIdx.x; base < total; base += kBatch * blockDim.x) {
-    float x[kBatch][8];
-    long long off[kBatch];
+    Raw8<TIn> raw[kBatch];
+    int off[kBatch];   // element offset from this CTA's first token (q or k tensor)
     int cs_idx[kBatch];
     bool live[kBatch], is_q[kBatch];
 #pragma unroll
@@ -93,22 +104,23 @@ __global__ void __launch_bounds__(256) rope_kernel(const TIn* __restrict__ xq, c
       live[u] = v < total && tok < n_tok;
       is_q[u] = r < vq;
       const int rr = is_q[u] ? r : r - vq;
-      off[u] = (tok * (is_q[u] ? Hq : Hk)) * kRopeDim + (long long)rr * 8;
+      off[u] = (p * (is_q[u] ? Hq : Hk)) * kRopeDim + rr * 8;
       cs_idx[u] = p * kRopePairs + (rr & 15) * 4;
-      if (live[u]) load8<TIn>((is_q[u] ? xq : xk) + off[u], x[u]);
+      if (live[u]) raw[u].load((is_q[u] ? xq + tok0 * Hq * kRopeDim : xk + tok0 * Hk * kRopeDim) + off[u]);
     }
 #pragma unroll
     for (int u = 0; u < kBatch; ++u) {
       if (!live[u]) continue;
-      float y[8];
+      float x[8], y[8];
+      raw[u].unpack(x);
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const float2 f = (&cs[0][0])[cs_idx[u] + i];
         // (a + ib)(c + is) = (ac - bs) + i(as + bc), separately rounded products as in a plain complex64 multiply
-        y[2 * i] = __fsub_rn(__fmul_rn(x[u][2 * i], f.x), __fmul_rn(x[u][2 * i + 1], f.y));
-        y[2 * i + 1] = __fadd_rn(__fmul_rn(x[u][2 * i], f.y), __fmul_rn(x[u][2 * i + 1], f.x));
+        y[2 * i] = __fsub_rn(__fmul_rn(x[2 * i], f.x), __fmul_rn(x[2 * i + 1], f.y));
+        y[2 * i + 1] = __fadd_rn(__fmul_rn(x[2 * i], f.y), __fmul_rn(x[2 * i + 1], f.x));
       }
-      store8<TOut>((is_q[u] ? oq : ok) + off[u], y);
+      store8<TOut>((is_q[u] ? oq + tok0 * Hq * kRopeDim : ok + tok0 * Hk * kRopeDim) + off[u], y);
     }
   }
 }

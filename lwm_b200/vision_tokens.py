@@ -50,18 +50,22 @@ def frame_tokens(codes, max_n_frames=-1, eof_token=EOF_TOKEN, eov_token=EOV_TOKE
     return out if batched else out[0]
 
 
+def _as_frames(t, P):
+    """view a token tensor as [..., n_frames, P+1]; a flat (1-D) stream is always split into frames"""
+    if t.dim() == 0 or t.shape[-1] % (P + 1):
+        raise _lib.LwmError("unframe_tokens: last dimension must be a multiple of tokens_per_frame + 1")
+    if t.dim() == 1 or t.shape[-1] != P + 1:
+        t = t.reshape(*t.shape[:-1], t.shape[-1] // (P + 1), P + 1)
+    return t
+
+
 def unframe_tokens(tokens, n_tokens_per_frame=N_TOKENS_PER_FRAME, grid=(16, 16)):
     """tokens int [..., T*(P+1)] or [..., T, P+1] -> codes int32 [..., T, 16, 16] with the per-frame delimiter dropped
     (vision_generation.py:160 `output[:, :-1].reshape(-1,16,16)`, :221 `output[:, :, :-1].reshape(-1,n_frames,16,16)`)."""
     if not tokens.is_cuda:
         raise _lib.LwmError("unframe_tokens: tokens must be a CUDA tensor (no CPU path)")
     P = n_tokens_per_frame
-    t = tokens.to(torch.int32)
-    if t.shape[-1] != P + 1:
-        if t.shape[-1] % (P + 1):
-            raise _lib.LwmError("unframe_tokens: last dimension must be a multiple of tokens_per_frame + 1")
-        t = t.reshape(*t.shape[:-1], t.shape[-1] // (P + 1), P + 1)
-    t = t.contiguous()
+    t = _as_frames(tokens.to(torch.int32), P).contiguous()
     lead = t.shape[:-1]
     n = int(np.prod(lead)) if len(lead) else 1
     out = torch.empty(*lead, P, dtype=torch.int32, device=t.device)

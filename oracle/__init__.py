@@ -10,6 +10,9 @@ PARITY STATUS
     (oracle/flax_shim, tools/make_golden_vqgan_from_reference.py); oracle/vqgan_ref.py reproduces it (indices
     bit-exact, floats to 1e-6). The semantics of the flax primitives themselves (nn.Conv SAME/HWIO, nn.GroupNorm
     defaults, nearest resize) are this repo's reading of flax 0.8.4 — not executable offline.
+  * RoPE (oracle/rope.py) and vision token framing (oracle/vision_tokens.py): PINNED — fixtures produced by executing
+    the reference's own functions / class (source text extracted at generation time from lwm/llama.py and lwm/data.py,
+    tools/make_golden_next_rows_from_reference.py); reproduced bit for bit.
   * Ring attention: UNPINNED — see below.
 PARITY UNPINNED (ring attention): the reference ships no tests / golden vectors, the ring-attention arithmetic
 lives in the un-vendored, un-pinned `ringattention` pip package (gpu_requirements.txt:8), and

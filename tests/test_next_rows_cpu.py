@@ -80,6 +80,16 @@ def test_vision_token_roundtrip_and_host_selection():
     assert select_frames(7, -1) is None and select_frames(7, 7) is None
     assert select_frames(9, 4).tolist() == np.linspace(0, 8, 4).astype(int).tolist()
     assert vision_mask(3, 1, 2) == V.vision_field(codes[:768], [0], [0, 0])[1]
+    # shape handling of the un-framing host code (pure views, no kernel)
+    import torch
+    from lwm_b200 import _lib
+    from lwm_b200.vision_tokens import _as_frames
+    assert _as_frames(torch.zeros(257), 256).shape == (1, 257)            # a single framed image, flat
+    assert _as_frames(torch.zeros(5 * 257), 256).shape == (5, 257)
+    assert _as_frames(torch.zeros(2, 257), 256).shape == (2, 257)         # vision_generation.py:159-160
+    assert _as_frames(torch.zeros(2, 3 * 257), 256).shape == (2, 3, 257)  # vision_generation.py:219-221
+    with pytest.raises(_lib.LwmError):
+        _as_frames(torch.zeros(300), 256)
 
 
 @pytest.mark.skipif(not os.path.exists("/root/reference/lwm/llama.py"), reason="reference tree only in the build container")

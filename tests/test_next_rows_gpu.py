@@ -1,7 +1,8 @@
 """GPU parity (through the C ABI) of the §8f next rows: rotary embedding of the attention prologue against the
 fixture produced by the reference's own `apply_rotary_emb`, and the vision token framing (bit-exact).
 Tolerances: fp32 output: |err| <= 1.5e-6 (cos/sin are within 1 ulp of the reference's table, inputs are O(1));
-bf16 output: equal to the fp32 oracle rounded to bf16 up to 1 bf16 ulp on rare rounding ties."""
+bf16 output: equal to the fp32 oracle rounded to bf16, except one bf16 ulp on rare rounding ties (near-cancelled
+results are compared on absolute error, their ulp being arbitrarily small)."""
 import os
 
 import numpy as np
@@ -43,10 +44,10 @@ def test_rope_bf16_io_and_large_shape():
     rq, rk = R.rope_reference(xq.float().numpy(), xk.float().numpy(), pos.numpy(), 5e7, 1 << 20)
     for got, ref in ((oq, rq), (ok, rk)):
         ref16 = torch.from_numpy(ref).to(torch.bfloat16)
-        diff = (got.cpu().view(torch.int16).int() - ref16.view(torch.int16).int()).abs()
-        assert int(diff.max()) <= 1                        # never more than one bf16 ulp
-        assert float((diff > 0).float().mean()) < 2e-3     # and only on rare ties
-        assert np.abs(to_np(got) - ref).max() <= 2.0 ** -7 * max(1.0, np.abs(ref).max())
+        differs = (got.cpu() != ref16)
+        assert float(differs.float().mean()) < 2e-3        # identical bf16 values except on rare rounding ties ...
+        err = np.abs(to_np(got) - ref)
+        assert (err <= 2.0 ** -8 * np.abs(ref) + 1e-6).all()  # ... which move by one bf16 ulp at most
 
 
 def test_rope_backward_is_the_conjugate_rotation():
