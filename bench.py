@@ -197,6 +197,8 @@ def main():
     ap.add_argument("--impl", default="lwm_b200")
     ap.add_argument("--seq", type=int, default=S_TOTAL, help="(debug) override the total sequence length")
     ap.add_argument("--layout", default="auto")
+    ap.add_argument("--precision", default=None, choices=[None, "bf16", "fp16"],
+                    help="attention precision mode (default: the package default, bf16)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-vqgan", action="store_true")
     args = ap.parse_args()
@@ -234,7 +236,9 @@ def main():
     kwargs = dict(axis_name="sp", float32_logits=True, cache_idx=None,
                   blockwise_kwargs=dict(causal_block_size=1, deterministic=True, dropout_rng=None, attn_pdrop=0.0,
                                         query_chunk_size=1024, key_chunk_size=1024, dtype=torch.bfloat16,
-                                        policy=None, precision=None, prevent_cse=True), layout=args.layout)
+                                        policy=None, precision=None, prevent_cse=True), layout=args.layout,
+                  precision=args.precision)
+    from lwm_b200 import _lib
 
     ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
     kern_ms = {"fwd": [], "bwd": []}
@@ -258,18 +262,19 @@ def main():
         sampler.start()
     t0, t1 = ev(), ev()
     barrier()
+    calls0 = _lib.launch_count()
     t0.record()
     for _ in range(K):
         step()
     t1.record()
     barrier()
+    gpu_launches = _lib.launch_count() - calls0      # C-ABI compute calls of this rank in the timed region
     ms = t0.elapsed_time(t1) / K
     clocks = sampler.stop() if rank == 0 else None
     if world > 1:
         tm = torch.tensor([ms], device=dev)
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
         ms = float(tm.item())
-    launches_per_step = 6 if world == 1 else None
 
     # ---- dominant-kernel timing (single GPU): the raw fwd / bwd tile kernels, CUDA events on their stream
     roof = None
@@ -359,13 +364,13 @@ def main():
             "dtype": "bf16", "data": "synthetic",
             "config": {"workload": "LWM-7B ring attention fwd+bwd, one layer, S=%d B=1 H=32 D=128 causal, "
                                    "sequence-sharded over %d GPU(s)" % (S, world),
-                       "layout": args.layout, "l2": "inputs (>=1 GiB per tensor at N=1) larger than the 126 MB L2",
+                       "layout": args.layout, "precision": args.precision or ra._DEFAULT_PRECISION, "l2": "inputs (>=1 GiB per tensor at N=1) larger than the 126 MB L2",
                        "tokens_per_s_definition": "S / (32 layers * t_step), attention only"},
             "tflops_per_gpu": total_flops / (ms * 1e-3) / 1e12 / world,
             "frac_of_bf16_peak_per_gpu": total_flops / (ms * 1e-3) / 1e12 / world / peaks["sustained"],
             "e2e": {"value": S / (LAYERS * ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": bytes_in, "d2h_bytes_per_step": bytes_out},
-            "gpu_launches": (launches_per_step * K) if launches_per_step else None,
+            "gpu_launches": gpu_launches,
             "clocks": clocks,
         }
         if roof:

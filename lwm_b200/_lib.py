@@ -68,8 +68,18 @@ def load():
     return lib
 
 
+_n_calls = 0
+
+
+def launch_count():
+    """number of C-ABI compute calls made by this process so far (each launches at least one kernel)"""
+    return _n_calls
+
+
 def call(name, *args):
+    global _n_calls
     lib = load()
+    _n_calls += 1
     status = getattr(lib, name)(*args)
     if status != 0:
         raise LwmError("%s failed (status %d): %s" % (name, status, lib.lwm_last_error().decode()))

@@ -124,3 +124,76 @@ def test_zigzag_plan_is_balanced_and_consistent():
                 assert sends == recvs
         contiguous = [sum(rs.work_units(rs.make_plan(P, r, 1024, 1024, True, "contiguous"), True)) for r in range(P)]
         assert max(contiguous) / (sum(contiguous) / P) > 1.4   # the imbalance zigzag removes
+
+
+def _worker_f16_plumbing(rank, world, port, ret):
+    """The fp16-precision ops wrapper (operand-conversion cache keyed by buffer address, fp32 output residuals) driven
+    through the real ring sequencing under gloo, with its three kernel entry points replaced by CPU emulations."""
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from lwm_b200 import ring_exec as rx, ring_schedule as rs, ringattention as ra
+        from oracle.step_ops import CpuOps
+        from oracle.attn_dense import attention_dense, attention_dense_grads, finfo_min
+
+        def to_f16(x):
+            e = torch.floor(torch.log2(x.abs().max()))
+            scale = torch.pow(torch.tensor(2.0), e - 12)
+            return (x / scale).half(), scale
+
+        def fwd_step(q16, k16, v16, out, lse, acc_o, acc_m, acc_l, q_pos0, k_pos0, causal, bias, seg, first, last,
+                     scales=None, out_f32=None):
+            sq, sk, sv = scales
+            CpuOps.fwd_step(q16.float() * sq, k16.float() * sk, v16.float() * sv, out, lse, acc_o, acc_m, acc_l,
+                            q_pos0, k_pos0, causal, bias, seg, first, last)
+            if out_f32 is not None:
+                out_f32.copy_(out)
+
+        def bwd_step(q16, k16, v16, d16, lse, delta, dq, dk, dv, q_pos0, k_pos0, causal, bias, seg, scales=None):
+            sq, sk, sv, sd = scales
+            CpuOps.bwd_step(q16.float() * sq, k16.float() * sk, v16.float() * sv, d16.float() * sd, lse, delta, dq, dk,
+                            dv, q_pos0, k_pos0, causal, bias, seg)
+        ra.to_f16, ra.fwd_step, ra.bwd_step = to_f16, fwd_step, bwd_step
+
+        class Ops(ra.CudaOpsF16):
+            bwd_prep = staticmethod(CpuOps.bwd_prep)
+            lse_for_bwd = staticmethod(CpuOps.lse_for_bwd)
+            cast = staticmethod(CpuOps.cast)
+            accumulate = staticmethod(CpuOps.accumulate)
+
+        B, S, H, D = 1, 256 * world, 2, 16
+        Sl = S // world
+        g = torch.Generator().manual_seed(7)
+        q, k, v, do = [torch.randn(B, S, H, D, generator=g) for _ in range(4)]
+        sl = slice(rank * Sl, (rank + 1) * Sl)
+        ks, vs = k[:, sl].contiguous(), v[:, sl].contiguous()
+        plan = rs.make_plan(world, rank, Sl, Sl, True, "zigzag")
+        ops = Ops()
+        out, res = rx.run_forward(plan, q[:, sl].contiguous(), ks, vs, None, None, True, None, ops)
+        n_cached = len(ops._cache)
+        res = ra._f32_residuals(ops, res)
+        assert all(o.dtype == torch.float32 for o in res["out_chunks"]) and len(ops.out_f32) == len(res["out_chunks"])
+        dq, dk, dv = rx.run_backward(plan, res, ks, vs, do[:, sl].contiguous(), None, None, True, None, Ops())
+        kw = dict(causal=True, attn_bias=None, segment_ids=None, mask_value=finfo_min("fp32"))
+        ref = attention_dense(q.numpy(), k.numpy(), v.numpy(), **kw)
+        rq, rk, rv = attention_dense_grads(q.numpy(), k.numpy(), v.numpy(), do.numpy(), **kw)
+
+        def err(x, r):
+            return float(np.linalg.norm(x.double().numpy() - r[:, sl]) / np.linalg.norm(r[:, sl]))
+        ret[rank] = (err(out, ref), err(dq, rq), err(dk, rk), err(dv, rv), n_cached,
+                     len(plan.q_chunks) + 2 * sum(len(st.kv) for st in plan.steps))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_fp16_precision_wrapper_through_the_ring(world):
+    ret = mp.Manager().dict()
+    mp.spawn(_worker_f16_plumbing, args=(world, _free_port(), ret), nprocs=world, join=True)
+    assert len(ret) == world
+    for r in range(world):
+        assert all(e < 2e-3 for e in ret[r][:4]), (r, ret[r])      # fp16-rounded operands: ~3e-4; a stale cache hit: O(1)
+        # every distinct operand block converted exactly once: the q chunks + K and V of every visible block
+        assert ret[r][4] == ret[r][5], ret[r]
