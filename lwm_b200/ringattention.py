@@ -33,7 +33,8 @@ _DEFAULT_PRECISION = os.environ.get("LWM_ATTN_PRECISION", "bf16")
 def set_default_precision(precision: str) -> None:
     """'bf16' (default): bf16 tensor-core operands, P/dS rounded to bf16 — the usual flash-attention numerics.
     'fp16': every operand is converted once to an exact power-of-two-scaled fp16 copy and P/dS keep 11
-    significant bits — ~8x lower rounding noise (meets 1e-3 on white-noise inputs) for ~3 % extra time."""
+    significant bits — ~8x lower rounding noise (meets 1e-3 on white-noise inputs) for ~1 % extra time (measured:
+    profiles/precision_perf_r01.log)."""
     global _DEFAULT_PRECISION
     if precision not in ("bf16", "fp16"):
         raise ValueError("precision must be 'bf16' or 'fp16'")
@@ -43,6 +44,25 @@ def set_default_precision(precision: str) -> None:
 def set_axis_group(axis_name: str, group) -> None:
     """Bind a mesh-axis name (the reference's 'sp') to a torch.distributed process group."""
     _AXIS_GROUPS[axis_name] = group
+
+
+def attention_bias_from_mask(attention_mask, dtype=torch.bfloat16):
+    """The call site's mask -> bias transform (lwm/llama.py:526, 532-537): attention_mask [B,S_global] (>0 = attend)
+    -> additive bias [B,1,1,S_global] in `dtype`: 0 where attended, finfo(dtype).min where not."""
+    m = attention_mask[:, None, None, :]
+    zero = torch.zeros((), dtype=dtype, device=m.device)
+    low = torch.full((), torch.finfo(dtype).min, dtype=dtype, device=m.device)
+    return torch.where(m > 0, zero, low)
+
+
+def decode_attention_mask(attention_mask, query_length, cache_index, max_decoder_length=None):
+    """Boolean mask [B,1,Q,K] for `ringattention_inference` while decoding from a KV cache (lwm/llama.py:574-591):
+    causal_mask[i, j] = j <= i + cache_index over the cache length, combined (AND) with the padding mask
+    attention_mask [B,K] (combine_masks)."""
+    K = attention_mask.shape[-1] if max_decoder_length is None else int(max_decoder_length)
+    dev = attention_mask.device
+    causal = torch.arange(K, device=dev)[None, :] <= (torch.arange(query_length, device=dev) + int(cache_index))[:, None]
+    return (attention_mask[:, None, None, :K] > 0) & causal[None, None]
 
 
 def _resolve_group(axis_name):
@@ -123,16 +143,23 @@ def ringattention(q, k, v, attn_bias=None, segment_ids=None, *, axis_name="sp", 
         raise NotImplementedError("cache_idx is always None at the reference call site (lwm/llama.py:544)")
     if not q.is_cuda:
         raise _lib.LwmError("ringattention: tensors must live on an sm_100 GPU (no CPU fallback)")
+    in_dtype = q.dtype
+    if in_dtype == torch.float32 and k.dtype == torch.float32 and v.dtype == torch.float32:
+        # the reference's scripts run dtype='fp32'; the tensor cores take 16-bit operands, so fp32 callers go through
+        # one rounding of q/k/v to bf16 (2^-9 relative) and get the output / gradients back in fp32
+        q, k, v = q.to(torch.bfloat16), k.to(torch.bfloat16), v.to(torch.bfloat16)
     if q.dtype != torch.bfloat16 or k.dtype != torch.bfloat16 or v.dtype != torch.bfloat16:
-        raise TypeError("ringattention: q, k, v must be bfloat16 (fp32 logits and accumulation are internal)")
+        raise TypeError("ringattention: q, k, v must all be bfloat16 or all float32 (fp32 logits and accumulation "
+                        "are internal)")
     B, Sq, H, D = q.shape
     causal = _check_blockwise_kwargs(blockwise_kwargs, Sq, k.shape[1])
     bias = _prep_bias(attn_bias, B)
     seg = None
     if segment_ids is not None:
         seg = segment_ids.to(torch.int32).contiguous()
-    return _RingAttnFn.apply(q.contiguous(), k.contiguous(), v.contiguous(), bias, seg, causal, axis_name, layout,
-                             precision)
+    out = _RingAttnFn.apply(q.contiguous(), k.contiguous(), v.contiguous(), bias, seg, causal, axis_name, layout,
+                            precision)
+    return out if in_dtype == torch.bfloat16 else out.to(in_dtype)
 
 
 # ------------------------------------------------------------------------------------------------

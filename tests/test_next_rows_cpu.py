@@ -105,3 +105,23 @@ def test_reference_functions_still_reproduce_the_fixtures(tmp_path):
         assert sorted(a.files) == sorted(b.files)
         for k in a.files:
             assert np.array_equal(a[k], b[k]), (name, k)
+
+
+def test_call_site_mask_helpers():
+    """host mirrors of lwm/llama.py:526-537 (mask -> additive finfo.min bias) and :574-591 (decode mask)"""
+    import torch
+    from lwm_b200.ringattention import attention_bias_from_mask, decode_attention_mask
+    m = torch.tensor([[0, 0, 1, 1, 1], [1, 1, 1, 1, 0]])
+    for dt in (torch.bfloat16, torch.float32):
+        b = attention_bias_from_mask(m, dt)
+        assert b.shape == (2, 1, 1, 5) and b.dtype == dt
+        assert b[0, 0, 0].tolist() == [torch.finfo(dt).min] * 2 + [0.0] * 3
+        assert b[1, 0, 0, -1].item() == torch.finfo(dt).min
+    # numpy restatement of llama.py:574-577, 586-587
+    Q, shift, K = 3, 4, 9
+    pad = np.ones((2, K), dtype=np.int64)
+    pad[0, :2] = 0
+    causal = np.arange(K)[None] <= (np.arange(Q) + shift)[:, None]
+    want = np.logical_and(np.broadcast_to(pad[:, None, None, :] > 0, (2, 1, Q, K)), causal[None, None])
+    got = decode_attention_mask(torch.from_numpy(pad), Q, shift)
+    assert got.dtype == torch.bool and np.array_equal(got.numpy(), want)
