@@ -1,13 +1,6 @@
-"""Import shim: `from ringattention import ringattention` (lwm/llama.py:30) resolves to the B200 op."""
+"""Import shim: `from ringattention import ringattention, blockwise_feedforward, ringattention_jax,
+ringattention_inference` (lwm/llama.py:30) resolves to the B200 ops."""
+from lwm_b200.blockwise_ffn import blockwise_feedforward  # noqa: F401
 from lwm_b200.ringattention import ringattention, ringattention_inference, set_axis_group  # noqa: F401
 
-
-def _not_built(name):
-    def f(*a, **k):
-        raise NotImplementedError("%s is outside the hot-path scope of lwm_b200 (SURVEY.md §8f next-rows)" % name)
-    f.__name__ = name
-    return f
-
-
-blockwise_feedforward = _not_built("blockwise_feedforward")
-ringattention_jax = ringattention
+ringattention_jax = ringattention      # the reference picks the pure-JAX variant off-TPU (llama.py:538); same op here

@@ -125,3 +125,28 @@ def test_call_site_mask_helpers():
     want = np.logical_and(np.broadcast_to(pad[:, None, None, :] > 0, (2, 1, Q, K)), causal[None, None])
     got = decode_attention_mask(torch.from_numpy(pad), Q, shift)
     assert got.dtype == torch.bool and np.array_equal(got.numpy(), want)
+
+
+def test_import_surface_of_the_ringattention_package_and_blockwise_ffn():
+    """lwm/llama.py:30 imports four names from `ringattention`; blockwise_feedforward == the un-chunked cell"""
+    import torch
+    from ringattention import blockwise_feedforward, ringattention, ringattention_inference, ringattention_jax
+    assert ringattention_jax is ringattention and callable(ringattention_inference)
+    torch.manual_seed(0)
+    w1, w2, w3 = [torch.randn(16, 64, requires_grad=True), torch.randn(64, 16, requires_grad=True),
+                  torch.randn(16, 64, requires_grad=True)]
+
+    def cell(x):                                     # the LLaMA MLP shape (llama.py:623-661): w2(silu(w1 x) * w3 x)
+        return (torch.nn.functional.silu(x @ w1) * (x @ w3)) @ w2
+    x = torch.randn(2, 32, 16, requires_grad=True)
+    ref = cell(x)
+    g = torch.randn_like(ref)
+    ref_grads = torch.autograd.grad(ref, (x, w1, w2, w3), g)
+    for pre_remat in (True, False):
+        out = blockwise_feedforward(cell, x, 8, pre_remat=pre_remat)
+        assert torch.allclose(out, ref, atol=1e-6)
+        grads = torch.autograd.grad(out, (x, w1, w2, w3), g)
+        for a, b in zip(grads, ref_grads):
+            assert torch.allclose(a, b, atol=1e-4, rtol=1e-5)
+    with pytest.raises(ValueError):
+        blockwise_feedforward(cell, x, 5)
