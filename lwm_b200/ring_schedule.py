@@ -61,6 +61,7 @@ class Plan:
     q_chunks: List[QRef]             # query chunks this rank computes
     q_sends: List[Tuple[int, int, int]]  # (start, length, peer): rows of MY shard computed elsewhere
     steps: List[Step]
+    params: Tuple = ()               # (Sq, Sk, causal, n_sub_first, n_sub_last): lets a rank re-derive a peer's plan
 
 
 def choose_layout(world, Sq, Sk, causal, layout):
@@ -148,7 +149,25 @@ def make_plan(world, rank, Sq, Sk, causal, layout="auto", n_sub_first=1, n_sub_l
                     if kv.owner == rank and any(visible(qc.pos0, qc.length, kv.pos0, causal) for qc in peer_q):
                         st.sends.append((kv.start, kv.length, peer))
             steps.append(st)
-    return Plan(world, rank, layout, q_chunks, q_sends, steps)
+    return Plan(world, rank, layout, q_chunks, q_sends, steps, (Sq, Sk, causal, n_sub_first, n_sub_last))
+
+
+def peer_plan(plan, peer):
+    """The plan rank `peer` derives for the same call (plans are pure functions of the call's shape)."""
+    Sq, Sk, causal, n_first, n_last = plan.params
+    return make_plan(plan.world, peer, Sq, Sk, causal, plan.layout, n_first, n_last)
+
+
+def landing_slots(plan):
+    """One-sided dK/dV return: every block of MY shard that a peer fetches at some step comes back as one fp32
+    partial (dk, dv). Slots are laid out in plan order -> {(step, peer, start, length): row offset} and the total
+    number of rows; a sender finds its slot with landing_slots(peer_plan(plan, owner))."""
+    table, rows = {}, 0
+    for idx, st in enumerate(plan.steps):
+        for (s, l, peer) in st.sends:
+            table[(idx, peer, s, l)] = rows
+            rows += l
+    return table, rows
 
 
 def work_units(plan, causal):

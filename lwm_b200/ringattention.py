@@ -24,6 +24,7 @@ import torch.distributed as dist
 
 from . import _lib
 from . import ring_exec as rx
+from . import ring_exec_symm as rxs
 from . import ring_schedule as rs
 
 _AXIS_GROUPS = {}
@@ -291,6 +292,15 @@ def _f32_residuals(ops, res):
     return res
 
 
+def _transport():
+    """'nccl' (default, the measured path: ring_exec.py) | 'symm' (EXPERIMENTAL one-sided pulls/puts over torch symmetric
+    memory, ring_exec_symm.py — validated on CPU emulation only so far)."""
+    t = os.environ.get("LWM_RING_TRANSPORT", "nccl")
+    if t not in ("nccl", "symm"):
+        raise ValueError("LWM_RING_TRANSPORT must be 'nccl' or 'symm'")
+    return t
+
+
 def _ops_for(precision):
     return CudaOpsF16() if precision == "fp16" else CudaOps
 
@@ -306,7 +316,10 @@ def ring_forward(q, k, v, bias, seg, causal, group, rank, world, layout="auto", 
         return out, _f32_residuals(ops, dict(q_chunks=[q], out_chunks=[out], lse_chunks=[lse]))
     lay = rs.choose_layout(world, Sq, k.shape[1], causal, layout)
     plan = rs.make_plan(world, rank, Sq, k.shape[1], causal, lay, n_sub_first=rs.auto_sub(world, k.shape[1], lay))
-    out, res = rx.run_forward(plan, q, k, v, bias, seg, causal, group, ops)
+    if _transport() == "symm":
+        out, res = rxs.run_forward(plan, q, k, v, bias, seg, causal, group, ops, rxs.SymmMemBackend.get(group, q.device))
+    else:
+        out, res = rx.run_forward(plan, q, k, v, bias, seg, causal, group, ops)
     return out, _f32_residuals(ops, res)
 
 
@@ -332,6 +345,8 @@ def ring_backward(res, k, v, dout, bias, seg, causal, group, rank, world, layout
     lay = rs.choose_layout(world, dout.shape[1], Sk, causal, layout)
     n_sub = rs.auto_sub(world, Sk, lay)
     plan = rs.make_plan(world, rank, dout.shape[1], Sk, causal, lay, n_sub_first=n_sub, n_sub_last=n_sub)
+    if _transport() == "symm":
+        return rxs.run_backward(plan, res, k, v, dout, bias, seg, causal, group, ops, rxs.SymmMemBackend.get(group, dev))
     return rx.run_backward(plan, res, k, v, dout, bias, seg, causal, group, ops)
 
 
