@@ -54,6 +54,7 @@ class SymmMemBackend:
             return
         import torch.distributed._symmetric_memory as symm
         nbytes = (nbytes + (1 << 21) - 1) >> 21 << 21
+        symm.enable_symm_mem_for_group(self.group.group_name)       # idempotent: registers the group's store
         self.buf = symm.empty(nbytes, dtype=torch.uint8, device=self.device)
         self.hdl = symm.rendezvous(self.buf, self.group)
         self.nbytes = nbytes
