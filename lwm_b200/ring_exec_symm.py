@@ -113,22 +113,25 @@ def _stage_kv(be, off, k, v):
 
 
 def _post_pulls(be, plan, off, k, v):
-    """post the pulls of EVERY step up front (K/V are immutable); -> per step (bufs, event)"""
+    """post the pulls of EVERY step up front (K/V are immutable); -> per step (bufs, event).
+    The receive buffers come from the MAIN stream's allocator pool (they are consumed there); the pull stream first
+    waits for everything already queued on the main stream, so a recycled block cannot still be in use."""
+    be.wait_event("pull", be.record("main"))
     out = []
     for st in plan.steps:
-        bufs = []
+        bufs, copies = [], []
+        for kv in st.kv:
+            if kv.owner == plan.rank:
+                bufs.append((rx._rows(k, kv.start, kv.length), rx._rows(v, kv.start, kv.length)))
+                continue
+            kb = torch.empty((k.shape[0], kv.length) + tuple(k.shape[2:]), dtype=k.dtype, device=k.device)
+            vb = torch.empty_like(kb)
+            bufs.append((kb, vb))
+            copies.append((kb, vb, kv))
         with be.on_pull_stream():
-            for kv in st.kv:
-                if kv.owner == plan.rank:
-                    bufs.append((rx._rows(k, kv.start, kv.length), rx._rows(v, kv.start, kv.length)))
-                    continue
-                src_k = be.view(kv.owner, off["k"], k.shape, k.dtype)[:, kv.start:kv.start + kv.length]
-                src_v = be.view(kv.owner, off["v"], v.shape, v.dtype)[:, kv.start:kv.start + kv.length]
-                kb = torch.empty((k.shape[0], kv.length) + tuple(k.shape[2:]), dtype=k.dtype, device=k.device)
-                vb = torch.empty_like(kb)
-                kb.copy_(src_k)
-                vb.copy_(src_v)
-                bufs.append((kb, vb))
+            for kb, vb, kv in copies:
+                kb.copy_(be.view(kv.owner, off["k"], k.shape, k.dtype)[:, kv.start:kv.start + kv.length])
+                vb.copy_(be.view(kv.owner, off["v"], v.shape, v.dtype)[:, kv.start:kv.start + kv.length])
             out.append((bufs, be.record("pull")))
     return out
 
@@ -198,6 +201,7 @@ def run_backward(plan, res, k, v, dout, bias, seg, causal, group, ops, be):
     pulls = _post_pulls(be, plan, off, k, v)
     _end_pass(be)
     slot_tables = {}
+    keep = []     # partials stay referenced until the put stream is done with them (they are main-stream allocations)
     for idx, st in enumerate(plan.steps):
         bufs, ev = pulls[idx]
         be.wait_event("main", ev)
@@ -246,6 +250,8 @@ def run_backward(plan, res, k, v, dout, bias, seg, causal, group, ops, be):
                     owners.append(kv.owner)
             for o in owners:
                 be.signal(o, 1 + idx)
+        keep.append(parts)
+    be.wait_event("main", be.record("put"))
     # fold in what the peers returned for my rows, in plan order (mostly landed while I was computing)
     my_slots, _ = rs.landing_slots(plan)
     land_dk = be.view(plan.rank, off["dk"], land_shape, torch.float32)
