@@ -6,6 +6,7 @@ The step functions are injected (`ops`), so the very same sequencing code is exe
 with the gloo backend and an oracle-backed `ops` in tests/test_ring_gloo.py, and on B200s with
 the CUDA C-ABI calls of lwm_b200.ringattention.
 """
+import os
 from typing import List
 
 import torch
@@ -177,6 +178,15 @@ def _post_step_kv(plan, comm, idx, k, v, after_event=None):
     return bufs, token
 
 
+def _prefetch_depth(n_steps):
+    """How many steps ahead the K/V exchange is posted. 1 (default, the measured configuration): step idx+1 is posted
+    when step idx starts. $LWM_RING_PREFETCH=all (or an integer): K/V are immutable during a pass, so every exchange
+    can be posted at the start of the pass — the transfers then no longer depend on each rank's host timing; costs the
+    whole remote K/V resident at once. Not yet measured on hardware."""
+    v = os.environ.get("LWM_RING_PREFETCH", "1")
+    return n_steps if v == "all" else max(1, min(int(v), n_steps))
+
+
 def run_forward(plan, q, k, v, bias, seg, causal, group, ops):
     """Returns (out [B,Sq,H,D] like q, residuals) with residuals = dict(q_chunks, out_chunks, lse_chunks)."""
     dev = q.device
@@ -198,11 +208,12 @@ def run_forward(plan, q, k, v, bias, seg, causal, group, ops):
             acc[qi] = (torch.empty(c.shape, dtype=torch.float32, device=dev),
                        torch.empty((B, H, c.shape[1]), dtype=torch.float32, device=dev),
                        torch.empty((B, H, c.shape[1]), dtype=torch.float32, device=dev))
-    nxt = _post_step_kv(plan, comm, 0, k, v)
+    depth = _prefetch_depth(len(plan.steps))
+    posted = [_post_step_kv(plan, comm, i, k, v) for i in range(depth)]
     for idx, st in enumerate(plan.steps):
-        bufs, token = nxt
-        if idx + 1 < len(plan.steps):
-            nxt = _post_step_kv(plan, comm, idx + 1, k, v)   # prefetch while this step computes
+        bufs, token = posted.pop(0)
+        if idx + depth < len(plan.steps):
+            posted.append(_post_step_kv(plan, comm, idx + depth, k, v))   # prefetch while this step computes
         comm.wait(token)
         for (qi, ki) in st.pairs:
             kb, vb = bufs[ki]
@@ -235,11 +246,12 @@ def run_backward(plan, res, k, v, dout, bias, seg, causal, group, ops):
     dv_acc = torch.zeros(v.shape, dtype=torch.float32, device=dev)
 
     pending = []   # (token, [(start, length, dk_buf, dv_buf)]) partials received from peers
-    nxt = _post_step_kv(plan, comm, 0, k, v)
+    depth = _prefetch_depth(len(plan.steps))
+    posted = [_post_step_kv(plan, comm, i, k, v) for i in range(depth)]
     for idx, st in enumerate(plan.steps):
-        bufs, token = nxt
-        if idx + 1 < len(plan.steps):
-            nxt = _post_step_kv(plan, comm, idx + 1, k, v)
+        bufs, token = posted.pop(0)
+        if idx + depth < len(plan.steps):
+            posted.append(_post_step_kv(plan, comm, idx + depth, k, v))
         comm.wait(token)
         parts = []
         for ki, kv in enumerate(st.kv):

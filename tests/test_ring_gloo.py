@@ -16,8 +16,9 @@ import torch.multiprocessing as mp
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _worker(rank, world, port, layout, use_masks, ret, n_sub=1, batch=1):
+def _worker(rank, world, port, layout, use_masks, ret, n_sub=1, batch=1, prefetch="1"):
     sys.path.insert(0, ROOT)
+    os.environ["LWM_RING_PREFETCH"] = prefetch
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -99,6 +100,17 @@ def test_sub_step_pipelined_plans_match_dense_oracle(world, layout):
     """first/last step cut in 2 sub-steps (transfer of piece j+1 overlaps the kernels of piece j)"""
     ret = mp.Manager().dict()
     mp.spawn(_worker, args=(world, _free_port(), layout, True, ret, 2), nprocs=world, join=True)
+    assert len(ret) == world
+    for r in range(world):
+        for e in ret[r]:
+            assert e < 1e-5, (r, ret[r])
+
+
+@pytest.mark.parametrize("world,layout,prefetch", [(4, "zigzag", "all"), (4, "contiguous", "2")])
+def test_deeper_kv_prefetch_matches_dense_oracle(world, layout, prefetch):
+    """LWM_RING_PREFETCH: every (or several) K/V exchange(s) posted ahead instead of one step ahead"""
+    ret = mp.Manager().dict()
+    mp.spawn(_worker, args=(world, _free_port(), layout, True, ret, 1, 1, prefetch), nprocs=world, join=True)
     assert len(ret) == world
     for r in range(world):
         for e in ret[r]:
