@@ -17,3 +17,15 @@ for _ in range(3):
     tok.encode(x)
 b.record(); torch.cuda.synchronize()
 print("encode %d frames (%s): %.2f ms" % (n, prec, a.elapsed_time(b) / 3))
+# decode of the same number of frames (codes -> pixels; 477.4 GFLOP / frame)
+codes = torch.randint(0, 8192, (n, 16, 16), dtype=torch.int32, device="cuda")
+for _ in range(2):
+    tok.decode(codes)
+torch.cuda.synchronize()
+a.record()
+for _ in range(3):
+    tok.decode(codes)
+b.record(); torch.cuda.synchronize()
+ms = a.elapsed_time(b) / 3
+print("decode %d frames (%s): %.2f ms = %.0f frames/s, %.0f algorithmic TFLOP/s" % (n, prec, ms, n / ms * 1e3,
+                                                                                  n * 477.4e9 / ms / 1e9))
