@@ -506,7 +506,6 @@ static int attn_bwd_launch(const void* q, const void* k, const void* v, const vo
                            long long bias_stride, const int* segment_ids, long long seg_stride, float softmax_scale,
                            const float* scale_q, const float* scale_k, const float* scale_v, const float* scale_do,
                            void* stream) {
-  if (!lwm_check_device()) return LWM_ERR_DEVICE;
   if (D != kHeadDim) return lwm_fail(LWM_ERR_SHAPE, "attn_bwd: head_dim must be 128");
   if (B <= 0 || H <= 0 || Sq <= 0 || Sk <= 0 || Sq % kTile || Sk % kTile)
     return lwm_fail(LWM_ERR_SHAPE, "attn_bwd: Sq and Sk must be positive multiples of 128");
@@ -514,6 +513,7 @@ static int attn_bwd_launch(const void* q, const void* k, const void* v, const vo
     return lwm_fail(LWM_ERR_ARG, "attn_bwd: null pointer");
   if (q_pos0 + Sq > 0x7fffffffLL || k_pos0 + Sk > 0x7fffffffLL)
     return lwm_fail(LWM_ERR_SHAPE, "attn_bwd: global positions must fit in int32");
+  if (!lwm_check_device()) return LWM_ERR_DEVICE;
   CUtensorMap tq, tk, tv, tdo, tdq;
   if (!make_bf16_tmap(&tq, q, B, Sq, H) || !make_bf16_tmap(&tk, k, B, Sk, H) || !make_bf16_tmap(&tv, v, B, Sk, H) ||
       !make_bf16_tmap(&tdo, dout, B, Sq, H) || !make_f32_tmap(&tdq, dq_acc, B, Sq, H))

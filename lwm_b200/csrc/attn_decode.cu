@@ -156,11 +156,11 @@ extern "C" int lwm_attn_decode_partial(const void* q, const void* k, const void*
                                        float* o_part, float* ml_part, void* workspace, int B, int H, int Q, int Sk,
                                        int D, long long k_pos0, long long mask_stride_b, long long mask_stride_q,
                                        int splits, float softmax_scale, void* stream) {
-  if (!lwm_check_device()) return LWM_ERR_DEVICE;
   if (D != kHeadDim) return lwm_fail(LWM_ERR_SHAPE, "attn_decode: head_dim must be 128");
   if (!q || !k || !v || !o_part || !ml_part || !workspace) return lwm_fail(LWM_ERR_ARG, "attn_decode: null pointer");
   if (B <= 0 || H <= 0 || Q <= 0 || Sk <= 0 || splits <= 0 || (long long)B * Q > 65535)
     return lwm_fail(LWM_ERR_SHAPE, "attn_decode: bad shape");
+  if (!lwm_check_device()) return LWM_ERR_DEVICE;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const long long rows = (long long)B * Q * H;
   float* ws_o = reinterpret_cast<float*>(workspace);
@@ -178,8 +178,8 @@ extern "C" int lwm_attn_decode_partial(const void* q, const void* k, const void*
 // merge n_part partials per row (e.g. the all-gathered per-rank partials) into out (bf16) and lse.
 extern "C" int lwm_attn_decode_merge(const float* o_parts, const float* ml_parts, int n_part, void* out, float* lse,
                                      long long rows, void* stream) {
-  if (!lwm_check_device()) return LWM_ERR_DEVICE;
   if (!o_parts || !ml_parts || !out || n_part <= 0 || rows <= 0) return lwm_fail(LWM_ERR_ARG, "attn_decode_merge: bad args");
+  if (!lwm_check_device()) return LWM_ERR_DEVICE;
   decode_merge_kernel<<<unsigned((rows + 3) / 4), 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       o_parts, ml_parts, n_part, reinterpret_cast<__nv_bfloat16*>(out), lse, nullptr, nullptr, rows);
   return lwm_check_launch("decode_merge_kernel");

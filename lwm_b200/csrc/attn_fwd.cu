@@ -420,7 +420,6 @@ static int attn_fwd_launch(const void* q, const void* k, const void* v, void* ou
                            const int* segment_ids, long long seg_stride, float softmax_scale, int first, int last,
                            const float* scale_q, const float* scale_k, const float* scale_v, float* out_f32,
                            void* stream) {
-  if (!lwm_check_device()) return LWM_ERR_DEVICE;
   if (D != kHeadDim) return lwm_fail(LWM_ERR_SHAPE, "attn_fwd: head_dim must be 128");
   if (B <= 0 || H <= 0 || Sq <= 0 || Sk <= 0 || Sq % kTile || Sk % kTile)
     return lwm_fail(LWM_ERR_SHAPE, "attn_fwd: Sq and Sk must be positive multiples of 128");
@@ -430,6 +429,7 @@ static int attn_fwd_launch(const void* q, const void* k, const void* v, void* ou
     return lwm_fail(LWM_ERR_ARG, "attn_fwd: carry buffers required unless first && last");
   if (q_pos0 + Sq > 0x7fffffffLL || k_pos0 + Sk > 0x7fffffffLL)
     return lwm_fail(LWM_ERR_SHAPE, "attn_fwd: global positions must fit in int32");
+  if (!lwm_check_device()) return LWM_ERR_DEVICE;
   CUtensorMap tq, tk, tv;
   if (!make_qkv_tmap(&tq, q, B, Sq, H) || !make_qkv_tmap(&tk, k, B, Sk, H) || !make_qkv_tmap(&tv, v, B, Sk, H))
     return lwm_fail(LWM_ERR_CUDA, "attn_fwd: cuTensorMapEncodeTiled failed (pointers must be 16B aligned)");

@@ -129,9 +129,9 @@ using namespace lwm;
 
 extern "C" int lwm_attn_bwd_prep(const void* out, const void* dout, float* delta, int B, int H, int Sq, int D,
                                  void* stream) {
-  if (!lwm_check_device()) return LWM_ERR_DEVICE;
   if (D != kHeadDim) return lwm_fail(LWM_ERR_SHAPE, "attn_bwd_prep: head_dim must be 128");
   if (!out || !dout || !delta) return lwm_fail(LWM_ERR_ARG, "attn_bwd_prep: null pointer");
+  if (!lwm_check_device()) return LWM_ERR_DEVICE;
   const long long rows = (long long)B * Sq * H;
   const int warps = 8;
   bwd_prep_kernel<<<unsigned((rows + warps - 1) / warps), warps * 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
@@ -141,9 +141,9 @@ extern "C" int lwm_attn_bwd_prep(const void* out, const void* dout, float* delta
 
 extern "C" int lwm_attn_bwd_prep_f32(const float* out_f32, const void* dout, float* delta, int B, int H, int Sq, int D,
                                      void* stream) {
-  if (!lwm_check_device()) return LWM_ERR_DEVICE;
   if (D != kHeadDim) return lwm_fail(LWM_ERR_SHAPE, "attn_bwd_prep_f32: head_dim must be 128");
   if (!out_f32 || !dout || !delta) return lwm_fail(LWM_ERR_ARG, "attn_bwd_prep_f32: null pointer");
+  if (!lwm_check_device()) return LWM_ERR_DEVICE;
   const long long rows = (long long)B * Sq * H;
   const int warps = 8;
   bwd_prep_f32_kernel<<<unsigned((rows + warps - 1) / warps), warps * 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
@@ -152,8 +152,8 @@ extern "C" int lwm_attn_bwd_prep_f32(const float* out_f32, const void* dout, flo
 }
 
 extern "C" int lwm_attn_bwd_lse(const float* lse, float* nlse2, long long n, void* stream) {
-  if (!lwm_check_device()) return LWM_ERR_DEVICE;
   if (!lse || !nlse2 || n <= 0) return lwm_fail(LWM_ERR_ARG, "attn_bwd_lse: bad args");
+  if (!lwm_check_device()) return LWM_ERR_DEVICE;
   const long long want = (n + 255) / 256;
   lse_to_nlse2_kernel<<<unsigned(want < 148LL * 8 ? want : 148LL * 8), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       lse, nlse2, n);
@@ -161,8 +161,8 @@ extern "C" int lwm_attn_bwd_lse(const float* lse, float* nlse2, long long n, voi
 }
 
 extern "C" int lwm_cast_f32_to_bf16(const float* src, void* dst, long long n, void* stream) {
-  if (!lwm_check_device()) return LWM_ERR_DEVICE;
   if (n % 4) return lwm_fail(LWM_ERR_SHAPE, "cast_f32_to_bf16: n must be a multiple of 4");
+  if (!lwm_check_device()) return LWM_ERR_DEVICE;
   if (n == 0) return LWM_OK;
   const long long n4 = n / 4;
   const int threads = 256;
@@ -174,8 +174,8 @@ extern "C" int lwm_cast_f32_to_bf16(const float* src, void* dst, long long n, vo
 }
 
 extern "C" int lwm_add_f32(float* dst, const float* src, long long n, void* stream) {
-  if (!lwm_check_device()) return LWM_ERR_DEVICE;
   if (n % 4) return lwm_fail(LWM_ERR_SHAPE, "add_f32: n must be a multiple of 4");
+  if (!lwm_check_device()) return LWM_ERR_DEVICE;
   if (n == 0) return LWM_OK;
   const long long n4 = n / 4;
   const int threads = 256;
@@ -189,9 +189,9 @@ extern "C" int lwm_add_f32(float* dst, const float* src, long long n, void* stre
 // bf16 tensor -> exact scaled fp16 copy + its power-of-two scale (device float). workspace: 4 bytes.
 extern "C" int lwm_attn_to_f16(const void* src_bf16, void* dst_f16, float* scale_out, void* workspace, long long n,
                                void* stream) {
-  if (!lwm_check_device()) return LWM_ERR_DEVICE;
   if (!src_bf16 || !dst_f16 || !scale_out || !workspace) return lwm_fail(LWM_ERR_ARG, "attn_to_f16: null pointer");
   if (n <= 0 || n % 8) return lwm_fail(LWM_ERR_SHAPE, "attn_to_f16: n must be a positive multiple of 8");
+  if (!lwm_check_device()) return LWM_ERR_DEVICE;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (cudaMemsetAsync(workspace, 0, 4, st) != cudaSuccess) return lwm_fail(LWM_ERR_CUDA, "attn_to_f16: memset failed");
   const long long n8 = n / 8;

@@ -142,13 +142,13 @@ using namespace lwm;
 extern "C" int lwm_attn_rope(const void* xq, const void* xk, int in_dtype, void* out_q, void* out_k, int out_dtype,
                              const int* position_ids, const float* inv_freq, int B, int S, int Hq, int Hk, int D,
                              int conj, void* stream) {
-  if (!lwm_check_device()) return LWM_ERR_DEVICE;
   if (D != kRopeDim) return lwm_fail(LWM_ERR_SHAPE, "attn_rope: head_dim must be 128");
   if (B <= 0 || S <= 0 || Hq <= 0 || Hk < 0) return lwm_fail(LWM_ERR_SHAPE, "attn_rope: bad sizes");
   if (!xq || !out_q || !position_ids || !inv_freq || (Hk > 0 && (!xk || !out_k)))
     return lwm_fail(LWM_ERR_ARG, "attn_rope: null pointer");
   if ((in_dtype != 0 && in_dtype != 1) || (out_dtype != 0 && out_dtype != 1))
     return lwm_fail(LWM_ERR_ARG, "attn_rope: dtype codes are 0 (fp32) or 1 (bf16)");
+  if (!lwm_check_device()) return LWM_ERR_DEVICE;
   const long long n_tok = (long long)B * S;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (in_dtype == 0 && out_dtype == 0)

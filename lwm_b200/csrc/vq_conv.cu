@@ -217,13 +217,13 @@ extern "C" int lwm_vq_conv2d(const void* a_hi, const void* a_lo, const void* w_h
                              const float* bias, const float* residual, float* out, int N, int Hin, int Win,
                              int Cpad, int Ho, int Wo, int Cout, int Cout_pad, int ksize, int stride, int pad,
                              int n_pass, int clip, void* stream) {
-  if (!lwm_check_device()) return LWM_ERR_DEVICE;
   if (!a_hi || !w_hi || !bias || !out) return lwm_fail(LWM_ERR_ARG, "vq_conv2d: null pointer");
   if (n_pass != 1 && n_pass != 3) return lwm_fail(LWM_ERR_ARG, "vq_conv2d: n_pass must be 1 (bf16) or 3 (bf16x3)");
   if (n_pass == 3 && (!a_lo || !w_lo)) return lwm_fail(LWM_ERR_ARG, "vq_conv2d: n_pass=3 needs the lo planes");
   if (Cpad % 64 || Cout_pad % 16 || Cout > Cout_pad) return lwm_fail(LWM_ERR_SHAPE, "vq_conv2d: Cpad % 64, Cout_pad % 16");
   if (Ho % 8 || Wo % 16) return lwm_fail(LWM_ERR_SHAPE, "vq_conv2d: output must tile by 8 x 16 pixels");
   if ((ksize != 1 && ksize != 3) || (stride != 1 && stride != 2)) return lwm_fail(LWM_ERR_SHAPE, "vq_conv2d: ksize 1|3, stride 1|2");
+  if (!lwm_check_device()) return LWM_ERR_DEVICE;
   int BN = Cout_pad;
   if (BN > 256) {
     if (Cout_pad % 256 == 0) BN = 256;

@@ -287,9 +287,9 @@ __global__ void vq_gather_kernel(const int* __restrict__ idx, const float4* __re
 using namespace lwm;
 
 extern "C" int lwm_vq_gn_stats(const float* x, double* stats, int N, int H, int W, int C, int groups, void* stream) {
-  if (!lwm_check_device()) return LWM_ERR_DEVICE;
   if (!x || !stats) return lwm_fail(LWM_ERR_ARG, "vq_gn_stats: null pointer");
   if (C % groups || (C / groups) % 4 || C % 4) return lwm_fail(LWM_ERR_SHAPE, "vq_gn_stats: C/groups must be a multiple of 4");
+  if (!lwm_check_device()) return LWM_ERR_DEVICE;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (cudaMemsetAsync(stats, 0, sizeof(double) * 2 * N * groups, st) != cudaSuccess)
     return lwm_fail(LWM_ERR_CUDA, "vq_gn_stats: memset failed");
@@ -307,11 +307,11 @@ extern "C" int lwm_vq_gn_stats(const float* x, double* stats, int N, int H, int 
 extern "C" int lwm_vq_prep(const float* x, const double* gn_stats, const float* gamma, const float* beta, void* hi,
                            void* lo, int N, int H, int W, int C, int C_pad, int groups, int upsample2x, float eps,
                            void* stream) {
-  if (!lwm_check_device()) return LWM_ERR_DEVICE;
   if (!x || !hi) return lwm_fail(LWM_ERR_ARG, "vq_prep: null pointer");
   if (C % 4 || C_pad % 8 || C_pad < C) return lwm_fail(LWM_ERR_SHAPE, "vq_prep: C % 4 and C_pad % 8 required");
   if (gn_stats && (!gamma || !beta || C % groups || (C / groups) % 4))
     return lwm_fail(LWM_ERR_SHAPE, "vq_prep: GroupNorm needs gamma/beta and C/groups % 4 == 0");
+  if (!lwm_check_device()) return LWM_ERR_DEVICE;
   const size_t total = (size_t)N * (H << upsample2x) * (W << upsample2x) * (C_pad / 8);
   const int threads = 256;
   const size_t want = (total + threads - 1) / threads;
@@ -324,10 +324,10 @@ extern "C" int lwm_vq_prep(const float* x, const double* gn_stats, const float* 
 
 extern "C" int lwm_vq_conv_cin3(const float* x, const float* w_hwio, const float* bias, float* y, int N, int H, int W,
                                 int Cout, void* stream) {
-  if (!lwm_check_device()) return LWM_ERR_DEVICE;
   if (!x || !w_hwio || !bias || !y) return lwm_fail(LWM_ERR_ARG, "vq_conv_cin3: null pointer");
   if (H % 8 || W % 16 || Cout != 128)
     return lwm_fail(LWM_ERR_SHAPE, "vq_conv_cin3: H % 8, W % 16 and Cout == 128 (hidden_channels, vqgan.py:64)");
+  if (!lwm_check_device()) return LWM_ERR_DEVICE;
   dim3 grid((H / 8) * (W / 16), N);
   conv_cin3_kernel<<<grid, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, w_hwio, bias, y, N, H, W);
   return lwm_check_launch("conv_cin3_kernel");
@@ -335,10 +335,10 @@ extern "C" int lwm_vq_conv_cin3(const float* x, const float* w_hwio, const float
 
 extern "C" int lwm_vq_argmin(const float* z, const float* codebook, int* idx, float* zq_st, void* workspace,
                              int N, int n_e, int e_dim, void* stream) {
-  if (!lwm_check_device()) return LWM_ERR_DEVICE;
   if (!z || !codebook || !idx || !workspace) return lwm_fail(LWM_ERR_ARG, "vq_argmin: null pointer");
   if (e_dim != kVqDim) return lwm_fail(LWM_ERR_SHAPE, "vq_argmin: e_dim must be 64 (quantized_embed_dim, vqgan.py:72)");
   if (N <= 0 || n_e <= 0) return lwm_fail(LWM_ERR_SHAPE, "vq_argmin: empty input");
+  if (!lwm_check_device()) return LWM_ERR_DEVICE;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   float* part_d = reinterpret_cast<float*>(workspace);            // workspace: 8 * N * (4 + 4) bytes
   int* part_i = reinterpret_cast<int*>(part_d + (size_t)kVqSplits * N);
@@ -350,9 +350,9 @@ extern "C" int lwm_vq_argmin(const float* z, const float* codebook, int* idx, fl
 
 extern "C" int lwm_vq_gather(const int* idx, const float* codebook, float* out, long long N, int n_e, int e_dim,
                              void* stream) {
-  if (!lwm_check_device()) return LWM_ERR_DEVICE;
   if (!idx || !codebook || !out) return lwm_fail(LWM_ERR_ARG, "vq_gather: null pointer");
   if (e_dim % 4) return lwm_fail(LWM_ERR_SHAPE, "vq_gather: e_dim % 4");
+  if (!lwm_check_device()) return LWM_ERR_DEVICE;
   if (N == 0) return LWM_OK;
   const int quads = e_dim / 4;
   const long long total = N * quads;

@@ -44,11 +44,11 @@ using namespace lwm;
 
 extern "C" int lwm_vq_frame_tokens(const int* codes, const int* frame_idx, int* tokens, int n_clips, int T_in, int T_out,
                                    int tokens_per_frame, int eof_token, int eov_token, void* stream) {
-  if (!lwm_check_device()) return LWM_ERR_DEVICE;
   if (!codes || !tokens) return lwm_fail(LWM_ERR_ARG, "vq_frame_tokens: null pointer");
   if (n_clips < 0 || T_in <= 0 || T_out <= 0 || tokens_per_frame <= 0)
     return lwm_fail(LWM_ERR_SHAPE, "vq_frame_tokens: a clip needs at least one frame");  // data.py:205 asserts n_frames > 0
   if (!frame_idx && T_in != T_out) return lwm_fail(LWM_ERR_SHAPE, "vq_frame_tokens: T_out != T_in needs frame_idx");
+  if (!lwm_check_device()) return LWM_ERR_DEVICE;
   if (n_clips == 0) return LWM_OK;
   const long long total = (long long)n_clips * T_out * (tokens_per_frame + 1);
   frame_tokens_kernel<<<grid_for(total), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
@@ -57,9 +57,9 @@ extern "C" int lwm_vq_frame_tokens(const int* codes, const int* frame_idx, int* 
 }
 
 extern "C" int lwm_vq_unframe_tokens(const int* tokens, int* codes, long long n_frames, int tokens_per_frame, void* stream) {
-  if (!lwm_check_device()) return LWM_ERR_DEVICE;
   if (!tokens || !codes) return lwm_fail(LWM_ERR_ARG, "vq_unframe_tokens: null pointer");
   if (n_frames < 0 || tokens_per_frame <= 0) return lwm_fail(LWM_ERR_SHAPE, "vq_unframe_tokens: bad sizes");
+  if (!lwm_check_device()) return LWM_ERR_DEVICE;
   if (n_frames == 0) return LWM_OK;
   const long long total = n_frames * tokens_per_frame;
   unframe_tokens_kernel<<<grid_for(total), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(tokens, codes, total,
