@@ -120,6 +120,11 @@ def cpu_sample_step(S, rows, heads, chunk=1024):
     return dt, flops
 
 
+def workload_name(S):
+    """one string for both arms (the reference arm runs on 'your arm's config')"""
+    return "LWM-7B ring attention fwd+bwd, one layer, S=%d B=1 H=32 D=128 causal" % S
+
+
 def run_reference_arm(args, rank):
     """`--impl reference`: the reference's own (CPU) algorithm for this path, restated in oracle/
     (the un-vendored JAX package cannot be installed offline — DESIGN.md), all host threads."""
@@ -142,7 +147,8 @@ def run_reference_arm(args, rank):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "LWM-7B attention fwd+bwd, S=131072, B=1, H=32, D=128, causal",
+        "config": {"workload": workload_name(S_TOTAL),
+                   "tokens_per_s_definition": "S / (32 layers * t_step), attention only",
                    "note": "CPU restatement of the reference algorithm (oracle/ring_blockwise.py); the JAX "
                            "reference cannot be installed offline"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
@@ -401,8 +407,7 @@ def main():
             "metric": METRIC, "value": S / (LAYERS * ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K,
             "warmup": W, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "LWM-7B ring attention fwd+bwd, one layer, S=%d B=1 H=32 D=128 causal, "
-                                   "sequence-sharded over %d GPU(s)" % (S, world),
+            "config": {"workload": workload_name(S), "sharding": "sequence over %d GPU(s)" % world,
                        "layout": args.layout, "precision": args.precision or ra._DEFAULT_PRECISION, "l2": "inputs (>=1 GiB per tensor at N=1) larger than the 126 MB L2",
                        "tokens_per_s_definition": "S / (32 layers * t_step), attention only"},
             "tflops_per_gpu": total_flops / (ms * 1e-3) / 1e12 / world,
