@@ -13,6 +13,8 @@ work is fixed as N grows.
           inputs and D2H copies of out/dq/dk/dv inside the timed region
   roofline   tensor-bound: algorithmic causal FLOPs of the dominant kernel (attn_bwd_kernel) per
           launch / its CUDA-event duration, against the measured cuBLAS bf16 peak
+  gpu_launches   C-ABI compute calls into liblwm_b200.so (each launches at least one of this repo's kernels) made by
+          rank 0 inside the timed region, counted by lwm_b200._lib.launch_count()
   cpu_baseline / --impl reference   the CPU restatement of the reference algorithm (oracle/),
           timed on the host cores on a bounded sample of the same workload.
 """
