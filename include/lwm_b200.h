@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define LWM_B200_ABI_VERSION 1
+#define LWM_B200_ABI_VERSION 2
 
 #define LWM_OK 0
 #define LWM_ERR_DEVICE 1
@@ -75,6 +75,8 @@ int lwm_attn_fwd_step(const void* q, const void* k, const void* v, void* out, fl
  *     dk_acc [B,Sk,H,D] fp32 += dS^T Q / sqrt(D)      (read-modify-write by the owning CTA)
  *     dv_acc [B,Sk,H,D] fp32 += P^T dO
  *   dk_acc/dv_acc travel with the K/V block around the ring exactly like the reference's dk, dv.
+ *   dkv_init != 0: the dk_acc/dv_acc rows of the key tiles this launch visits are WRITTEN instead of accumulated
+ *   (first visit of a block: saves zero-filling the accumulators); key tiles no query row can see are zero-filled.
  */
 int lwm_attn_bwd_prep(const void* out, const void* dout, float* delta, int B, int H, int Sq, int D, void* stream);
 int lwm_attn_bwd_lse(const float* lse, float* nlse2, long long n, void* stream);
@@ -82,7 +84,7 @@ int lwm_attn_bwd_step(const void* q, const void* k, const void* v, const void* d
                       const float* delta, float* dq_acc, float* dk_acc, float* dv_acc, int B, int H, int Sq,
                       int Sk, int D, long long q_pos0, long long k_pos0, int causal, const float* bias,
                       long long bias_stride, const int* segment_ids, long long seg_stride, float softmax_scale,
-                      void* stream);
+                      int dkv_init, void* stream);
 
 /* fp16-internal precision mode (optional): the tensor cores take bf16 x bf16 or fp16 x fp16 only, so the
  * higher-precision mode converts every operand once to an exact, power-of-two-scaled fp16 copy
@@ -103,7 +105,24 @@ int lwm_attn_bwd_step_f16(const void* q16, const void* k16, const void* v16, con
                           const float* delta, float* dq_acc, float* dk_acc, float* dv_acc, int B, int H, int Sq, int Sk,
                           int D, long long q_pos0, long long k_pos0, int causal, const float* bias,
                           long long bias_stride, const int* segment_ids, long long seg_stride, float softmax_scale,
-                          void* stream);
+                          int dkv_init, void* stream);
+
+/* Sharded-tensor variant of the fp16 operand conversion (ring executor): every rank publishes the |max| bit pattern of
+ * its shard (lwm_attn_absmax: atomicMax into *out_bits, caller zeroes it; dtype 0 = fp32, 1 = bf16), all ranks derive
+ * the SAME power-of-two scale from the gathered patterns (lwm_attn_scale_from_absmax over bits[i*stride], i < n), and
+ * convert with it (lwm_attn_to_f16_scaled: dst = fp16(x / *scale); an fp32 source — the dtype the reference's scripts
+ * run with — is rounded ONCE to fp16's 11 significant bits instead of going through bf16's 8).
+ * lwm_attn_bwd_prep_f16: delta = rowsum(out o dout) with dout given as its scaled fp16 copy; out fp32 (0) or bf16 (1).
+ * lwm_reduce_cast_f32: dst = cast(sum of n_src <= 16 fp32 arrays, fixed order) — folds the dK/dV partials that
+ * landed in the owner's heap and writes the gradient in its final dtype (0 fp32, 1 bf16) in one pass. host_srcs is a
+ * HOST array of device pointers. */
+#define LWM_REDUCE_MAX_SRCS 16
+int lwm_attn_absmax(const void* x, int dtype, long long n, unsigned* out_bits, void* stream);
+int lwm_attn_scale_from_absmax(const unsigned* bits, int n, int stride, float* scale_out, void* stream);
+int lwm_attn_to_f16_scaled(const void* x, int dtype, void* dst_f16, const float* scale, long long n, void* stream);
+int lwm_attn_bwd_prep_f16(const void* out, int out_dtype, const void* dout16, const float* scale_do, float* delta, int B,
+                          int H, int Sq, int D, void* stream);
+int lwm_reduce_cast_f32(const float* const* host_srcs, int n_src, void* dst, int dst_dtype, long long n, void* stream);
 
 /* Decode-time attention — the reference's `ringattention_inference(q, k, v, attn_mask, axis_name)` (call site
  * lwm/llama.py:601-614): a few query rows against this rank's KV-cache shard with an
@@ -135,6 +154,39 @@ int lwm_attn_rope(const void* xq, const void* xk, int in_dtype, void* out_q, voi
 int lwm_cast_f32_to_bf16(const float* src, void* dst, long long n, void* stream);
 /* dst[i] += src[i] (fp32, n % 4 == 0): folds a dK/dV partial received from a peer into the owner's accumulator. */
 int lwm_add_f32(float* dst, const float* src, long long n, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Peer-memory ring context — what replaces the reference's `lax.ppermute(k, v)` ring exchange (un-vendored
+ * `ringattention` package, entered at lwm/llama.py:539-569; SURVEY.md §8b "Ring-attn C ABI", §8e).
+ * On an NVSwitch box the ring is a schedule, not a topology: every rank owns one heap (cudaMalloc + cudaIpc handle)
+ * that all peers map; K/V (and Q/dO) blocks are PULLED out of the owner's heap and dK/dV partials / O / dQ chunks are
+ * PUT into landing slots of the owner's heap with copy-engine transfers (no SMs, no matching call on the peer), ordered
+ * by 32-bit flags living in the heaps: lwm_ring_signal = remote flag write enqueued behind the payload on the same
+ * stream, lwm_ring_wait = cuStreamWaitValue32(>=) on the local flag. No host synchronisation on the data path.
+ *
+ * Bootstrap (host side, once per process group): every rank calls lwm_ring_ctx_create, exchanges the
+ * LWM_RING_HANDLE_BYTES-byte handle of lwm_ring_ctx_get_handle with all peers by any means (torch.distributed
+ * all_gather here), then lwm_ring_ctx_open_peers(handles of all ranks, rank-major).
+ * signal_mode: how the remote flag write is issued — 0 cuStreamWriteValue32 on the peer mapping (default),
+ * 1 cuMemsetD32Async, 2 a 4-byte copy-engine transfer (values < 4096); all three were measured on B200 + NVSwitch
+ * (profiles/probe_ipc_n2_r02.log).
+ * Ownership: the context owns the heap and the mappings; everything else stays caller-owned. Not thread-safe
+ * (one host thread per rank). lwm_ring_ctx_heap(ctx, peer) is the address, valid in THIS process, of rank `peer`'s
+ * heap payload (the layout inside it is the caller's: lwm_b200/ring_peer.py documents the one the op uses). */
+typedef struct lwm_ring_ctx lwm_ring_ctx;
+#define LWM_RING_HANDLE_BYTES 64
+#define LWM_RING_MAX_WORLD 16
+#define LWM_RING_FLAG_BYTES 65536
+#define LWM_RING_NUM_FLAGS (LWM_RING_FLAG_BYTES / 4)
+int lwm_ring_ctx_create(int rank, int world, long long heap_bytes, int signal_mode, lwm_ring_ctx** ctx);
+int lwm_ring_ctx_get_handle(lwm_ring_ctx* ctx, void* handle64);
+int lwm_ring_ctx_open_peers(lwm_ring_ctx* ctx, const void* handles /* world * LWM_RING_HANDLE_BYTES */);
+void* lwm_ring_ctx_heap(lwm_ring_ctx* ctx, int peer);
+long long lwm_ring_ctx_heap_bytes(lwm_ring_ctx* ctx);
+int lwm_ring_copy(void* dst, const void* src, long long bytes, void* stream);
+int lwm_ring_signal(lwm_ring_ctx* ctx, int peer, int flag, unsigned value, void* stream);
+int lwm_ring_wait(lwm_ring_ctx* ctx, int flag, unsigned value, void* stream);
+int lwm_ring_ctx_destroy(lwm_ring_ctx* ctx);
 
 /* ---------------------------------------------------------------------------------------------
  * VQGAN tokenizer (lwm/vqgan.py:105-351). Activations are NHWC fp32 (flax layout and dtype).

@@ -19,13 +19,25 @@ _SIGNATURES = {
     "lwm_attn_bwd_prep": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
     "lwm_attn_bwd_lse": [c_void_p, c_void_p, c_ll, c_void_p],
     "lwm_attn_bwd_step": [c_void_p] * 9 + [c_int] * 5 + [c_ll, c_ll, c_int, c_void_p, c_ll, c_void_p, c_ll,
-                                                       c_float, c_void_p],
+                                                       c_float, c_int, c_void_p],
     "lwm_attn_to_f16": [c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_void_p],
     "lwm_attn_bwd_prep_f32": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
     "lwm_attn_fwd_step_f16": [c_void_p] * 12 + [c_int] * 5 + [c_ll, c_ll, c_int, c_void_p, c_ll, c_void_p, c_ll,
                                                              c_float, c_int, c_int, c_void_p],
     "lwm_attn_bwd_step_f16": [c_void_p] * 13 + [c_int] * 5 + [c_ll, c_ll, c_int, c_void_p, c_ll, c_void_p, c_ll,
-                                                             c_float, c_void_p],
+                                                             c_float, c_int, c_void_p],
+    "lwm_attn_absmax": [c_void_p, c_int, c_ll, c_void_p, c_void_p],
+    "lwm_attn_scale_from_absmax": [c_void_p, c_int, c_int, c_void_p, c_void_p],
+    "lwm_attn_to_f16_scaled": [c_void_p, c_int, c_void_p, c_void_p, c_ll, c_void_p],
+    "lwm_attn_bwd_prep_f16": [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
+    "lwm_reduce_cast_f32": [c_void_p, c_int, c_void_p, c_int, c_ll, c_void_p],
+    "lwm_ring_ctx_create": [c_int, c_int, c_ll, c_int, c_void_p],
+    "lwm_ring_ctx_get_handle": [c_void_p, c_void_p],
+    "lwm_ring_ctx_open_peers": [c_void_p, c_void_p],
+    "lwm_ring_copy": [c_void_p, c_void_p, c_ll, c_void_p],
+    "lwm_ring_signal": [c_void_p, c_int, c_int, ctypes.c_uint, c_void_p],
+    "lwm_ring_wait": [c_void_p, c_int, ctypes.c_uint, c_void_p],
+    "lwm_ring_ctx_destroy": [c_void_p],
     "lwm_attn_decode_partial": [c_void_p] * 7 + [c_int] * 5 + [c_ll, c_ll, c_ll, c_int, c_float, c_void_p],
     "lwm_attn_decode_merge": [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_ll, c_void_p],
     "lwm_cast_f32_to_bf16": [c_void_p, c_void_p, c_ll, c_void_p],
@@ -64,6 +76,10 @@ def load():
             continue  # exported-symbol coverage is asserted by tests/test_abi.py
         fn.restype = c_int
         fn.argtypes = argtypes
+    lib.lwm_ring_ctx_heap.restype = c_void_p           # address (in this process) of a rank's heap payload
+    lib.lwm_ring_ctx_heap.argtypes = [c_void_p, c_int]
+    lib.lwm_ring_ctx_heap_bytes.restype = c_ll
+    lib.lwm_ring_ctx_heap_bytes.argtypes = [c_void_p]
     _lib = lib
     return lib
 
@@ -76,10 +92,14 @@ def launch_count():
     return _n_calls
 
 
+_NOT_COMPUTE = ("lwm_ring_",)      # transport / bootstrap calls launch no kernel of ours
+
+
 def call(name, *args):
     global _n_calls
     lib = load()
-    _n_calls += 1
+    if not name.startswith(_NOT_COMPUTE):
+        _n_calls += 1
     status = getattr(lib, name)(*args)
     if status != 0:
         raise LwmError("%s failed (status %d): %s" % (name, status, lib.lwm_last_error().decode()))

@@ -43,6 +43,7 @@ struct BwdParams {
   float* dv_acc;       // [B,Sk,H,D] fp32
   unsigned long long* prof;  // debug wait-time buffer or null
   const float *scale_q, *scale_k, *scale_v, *scale_do;   // fp16 mode: device scalars (x = x16 * scale); else null
+  int dkv_init;        // 1: dk_acc/dv_acc rows of this launch are WRITTEN (first visit of the block), 0: accumulated
 };
 
 constexpr int kBwdThreads = 512;
@@ -96,7 +97,17 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     i_start = diff <= 0 ? 0 : int(min(diff / kTile, (long long)n_q_tiles));
   }
   const int nq = n_q_tiles - i_start;
-  if (nq <= 0) return;  // this key tile is invisible to the whole q shard: dk/dv unchanged
+  if (nq <= 0) {  // this key tile is invisible to the whole q shard: dk/dv unchanged (zero when this launch initialises them)
+    if (p.dkv_init) {
+      const long long base = (((long long)b * p.Sk + (long long)n * kTile) * p.H + h) * kHeadDim;
+      for (int i = threadIdx.x; i < kTile * kHeadDim / 4; i += kBwdThreads) {
+        const long long off = base + (long long)(i / (kHeadDim / 4)) * p.H * kHeadDim + (i % (kHeadDim / 4)) * 4;
+        *reinterpret_cast<float4*>(p.dk_acc + off) = make_float4(0.f, 0.f, 0.f, 0.f);
+        *reinterpret_cast<float4*>(p.dv_acc + off) = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+    return;
+  }
 
   if (warp == 9) {
     tmem_alloc<512>(&tmem_base_s);
@@ -467,7 +478,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         float4* dst = reinterpret_cast<float4*>(acc + c * 32);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          float4 cur = dst[i];
+          float4 cur = p.dkv_init ? make_float4(0.f, 0.f, 0.f, 0.f) : dst[i];
           cur.x = fmaf(__uint_as_float(o[4 * i]), acc_mul, cur.x);
           cur.y = fmaf(__uint_as_float(o[4 * i + 1]), acc_mul, cur.y);
           cur.z = fmaf(__uint_as_float(o[4 * i + 2]), acc_mul, cur.z);
@@ -505,7 +516,7 @@ static int attn_bwd_launch(const void* q, const void* k, const void* v, const vo
                            int Sk, int D, long long q_pos0, long long k_pos0, int causal, const float* bias,
                            long long bias_stride, const int* segment_ids, long long seg_stride, float softmax_scale,
                            const float* scale_q, const float* scale_k, const float* scale_v, const float* scale_do,
-                           void* stream) {
+                           int dkv_init, void* stream) {
   if (D != kHeadDim) return lwm_fail(LWM_ERR_SHAPE, "attn_bwd: head_dim must be 128");
   if (B <= 0 || H <= 0 || Sq <= 0 || Sk <= 0 || Sq % kTile || Sk % kTile)
     return lwm_fail(LWM_ERR_SHAPE, "attn_bwd: Sq and Sk must be positive multiples of 128");
@@ -528,6 +539,7 @@ static int attn_bwd_launch(const void* q, const void* k, const void* v, const vo
   p.lse = lse; p.delta = delta; p.dk_acc = dk_acc; p.dv_acc = dv_acc;
   p.prof = lwm_prof_buffer();
   p.scale_q = scale_q; p.scale_k = scale_k; p.scale_v = scale_v; p.scale_do = scale_do;
+  p.dkv_init = dkv_init ? 1 : 0;
   static bool attr_set = false;
   if (!attr_set) {
     if (cudaFuncSetAttribute(attn_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmemBytes) !=
@@ -548,9 +560,10 @@ extern "C" int lwm_attn_bwd_step(const void* q, const void* k, const void* v, co
                                  const float* delta, float* dq_acc, float* dk_acc, float* dv_acc, int B, int H,
                                  int Sq, int Sk, int D, long long q_pos0, long long k_pos0, int causal,
                                  const float* bias, long long bias_stride, const int* segment_ids,
-                                 long long seg_stride, float softmax_scale, void* stream) {
+                                 long long seg_stride, float softmax_scale, int dkv_init, void* stream) {
   return attn_bwd_launch(q, k, v, dout, lse, delta, dq_acc, dk_acc, dv_acc, B, H, Sq, Sk, D, q_pos0, k_pos0, causal,
-                         bias, bias_stride, segment_ids, seg_stride, softmax_scale, nullptr, nullptr, nullptr, nullptr, stream);
+                         bias, bias_stride, segment_ids, seg_stride, softmax_scale, nullptr, nullptr, nullptr, nullptr,
+                         dkv_init, stream);
 }
 
 // fp16-operand variant: scale_* = device scalars of the four fp16 operand copies (lwm_attn_to_f16).
@@ -560,9 +573,9 @@ extern "C" int lwm_attn_bwd_step_f16(const void* q16, const void* k16, const voi
                                      float* dk_acc, float* dv_acc, int B, int H, int Sq, int Sk, int D,
                                      long long q_pos0, long long k_pos0, int causal, const float* bias,
                                      long long bias_stride, const int* segment_ids, long long seg_stride,
-                                     float softmax_scale, void* stream) {
+                                     float softmax_scale, int dkv_init, void* stream) {
   if (!scale_q || !scale_k || !scale_v || !scale_do) return lwm_fail(LWM_ERR_ARG, "attn_bwd_f16: scales required");
   return attn_bwd_launch(q16, k16, v16, dout16, lse, delta, dq_acc, dk_acc, dv_acc, B, H, Sq, Sk, D, q_pos0, k_pos0,
                          causal, bias, bias_stride, segment_ids, seg_stride, softmax_scale, scale_q, scale_k, scale_v,
-                         scale_do, stream);
+                         scale_do, dkv_init, stream);
 }

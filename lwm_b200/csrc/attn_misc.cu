@@ -3,7 +3,9 @@
 //                         custom_vjp bwd, SURVEY.md Appendix A `bwd`)
 //   lwm_cast_f32_to_bf16  final cast of the fp32 gradient accumulators to the input dtype
 #include "attn_common.cuh"
+#include <cuda_fp16.h>
 #include "capi_internal.h"
+#include "../../include/lwm_b200.h"
 
 namespace lwm {
 
@@ -123,6 +125,103 @@ __global__ void bf16_to_scaled_f16_kernel(const uint4* __restrict__ x, uint4* __
   }
 }
 
+
+// |x| max over an fp32 tensor as raw bits
+__global__ void absmax_f32_kernel(const uint4* __restrict__ x, long long n4, unsigned* __restrict__ out_bits) {
+  unsigned m = 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
+       i += (long long)gridDim.x * blockDim.x) {
+    const uint4 v = x[i];
+    m = max(max(m, v.x & 0x7fffffffu), max(v.y & 0x7fffffffu, max(v.z & 0x7fffffffu, v.w & 0x7fffffffu)));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m) atomicMax(out_bits, m);
+}
+
+// scale = 2^(e-12), e = exponent of max_i bits[i*stride] (1.0 for all-zero): one thread. The ring executor feeds it
+// the |max| bit patterns of every rank's shard, so that all ranks derive the SAME scale for a sharded tensor.
+__global__ void scale_from_absmax_kernel(const unsigned* __restrict__ bits, int n, int stride, float* __restrict__ scale_out) {
+  unsigned m = 0;
+  for (int i = 0; i < n; ++i) m = max(m, bits[(long long)i * stride]);
+  const int e = max(int(m >> 23) - 127, -114);   // keeps 2^(e-12) a normal float
+  *scale_out = m ? __uint_as_float(unsigned(127 + (e - 12)) << 23) : 1.0f;
+}
+
+// x16 = fp16(x / *scale) for a power-of-two scale held on the device; source bf16 (exact for every value above
+// 2^-26 of the scale's tensor maximum) or fp32 (one rounding to fp16's 11 significant bits).
+__global__ void bf16_to_f16_by_scale_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, long long n8,
+                                            const float* __restrict__ scale) {
+  const float inv = 1.0f / *scale;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8;
+       i += (long long)gridDim.x * blockDim.x) {
+    const uint4 v = x[i];
+    const unsigned w[4] = {v.x, v.y, v.z, v.w};
+    unsigned o[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      o[k] = pack_f16x2(__uint_as_float(w[k] << 16) * inv, __uint_as_float(w[k] & 0xffff0000u) * inv);
+    y[i] = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+__global__ void f32_to_f16_by_scale_kernel(const float4* __restrict__ x, uint2* __restrict__ y, long long n4,
+                                           const float* __restrict__ scale) {
+  const float inv = 1.0f / *scale;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
+       i += (long long)gridDim.x * blockDim.x) {
+    const float4 v = x[i];
+    y[i] = make_uint2(pack_f16x2(v.x * inv, v.y * inv), pack_f16x2(v.z * inv, v.w * inv));
+  }
+}
+
+// delta = rowsum(out o dout) with dout given as the scaled fp16 operand copy (dout = dout16 * *scale_do) and out in
+// fp32 (kOutF32) or bf16: the ring executor only ever holds the fp16 copy of a remote dO chunk.
+template <bool kOutF32>
+__global__ void bwd_prep_f16_kernel(const void* __restrict__ out, const __half* __restrict__ dout16,
+                                    const float* __restrict__ scale_do, float* __restrict__ delta, int B, int H, int S) {
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long n_rows = (long long)B * S * H;
+  if (row >= n_rows) return;
+  const int lane = threadIdx.x & 31;
+  float a[4];
+  if (kOutF32) {
+    const float4 t = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(out) + row * kHeadDim)[lane];
+    a[0] = t.x; a[1] = t.y; a[2] = t.z; a[3] = t.w;
+  } else {
+    const uint2 t = reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(out) + row * kHeadDim)[lane];
+    a[0] = __uint_as_float(t.x << 16); a[1] = __uint_as_float(t.x & 0xffff0000u);
+    a[2] = __uint_as_float(t.y << 16); a[3] = __uint_as_float(t.y & 0xffff0000u);
+  }
+  const uint2 g = reinterpret_cast<const uint2*>(dout16 + row * kHeadDim)[lane];
+  const __half2 g0 = *reinterpret_cast<const __half2*>(&g.x);
+  const __half2 g1 = *reinterpret_cast<const __half2*>(&g.y);
+  float acc = a[0] * __low2float(g0) + a[1] * __high2float(g0) + a[2] * __low2float(g1) + a[3] * __high2float(g1);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) {
+    const int h = int(row % H);
+    const long long bs = row / H;
+    delta[((long long)(bs / S) * H + h) * S + (bs % S)] = acc * (*scale_do);
+  }
+}
+
+// dst = cast(sum_i srcs[i]) : folds the dK/dV partials that landed in the owner's heap (plus the owner's own partial)
+// and produces the gradient in its final dtype in ONE pass (fp32 sum in a fixed order -> run-to-run deterministic).
+struct ReduceSrcs { const float4* p[LWM_REDUCE_MAX_SRCS]; };
+template <bool kToBf16>
+__global__ void reduce_cast_kernel(const ReduceSrcs srcs, int n_src, void* __restrict__ dst, long long n4) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
+       i += (long long)gridDim.x * blockDim.x) {
+    float4 a = srcs.p[0][i];
+    for (int s = 1; s < n_src; ++s) {
+      const float4 b = srcs.p[s][i];
+      a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    }
+    if (kToBf16) reinterpret_cast<uint2*>(dst)[i] = make_uint2(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w));
+    else reinterpret_cast<float4*>(dst)[i] = a;
+  }
+}
+
 }  // namespace lwm
 
 using namespace lwm;
@@ -203,4 +302,67 @@ extern "C" int lwm_attn_to_f16(const void* src_bf16, void* dst_f16, float* scale
                                                     reinterpret_cast<uint4*>(dst_f16), n8,
                                                     reinterpret_cast<const unsigned*>(workspace), scale_out);
   return lwm_check_launch("attn_to_f16 kernels");
+}
+
+
+static unsigned grid_for(long long items, int threads, int waves) {
+  const long long want = (items + threads - 1) / threads;
+  return unsigned(want < 148LL * waves ? (want > 0 ? want : 1) : 148LL * waves);
+}
+
+// atomicMax of the |x| bit patterns into *out_bits (the caller zeroes it); dtype 0 = fp32, 1 = bf16.
+extern "C" int lwm_attn_absmax(const void* x, int dtype, long long n, unsigned* out_bits, void* stream) {
+  if (!x || !out_bits || n <= 0 || n % 8 || (dtype != 0 && dtype != 1)) return lwm_fail(LWM_ERR_ARG, "attn_absmax: bad arguments (n % 8 == 0)");
+  if (!lwm_check_device()) return LWM_ERR_DEVICE;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (dtype == 1) absmax_bf16_kernel<<<grid_for(n / 8, 256, 8), 256, 0, st>>>(reinterpret_cast<const uint4*>(x), n / 8, out_bits);
+  else absmax_f32_kernel<<<grid_for(n / 4, 256, 8), 256, 0, st>>>(reinterpret_cast<const uint4*>(x), n / 4, out_bits);
+  return lwm_check_launch("absmax kernel");
+}
+
+extern "C" int lwm_attn_scale_from_absmax(const unsigned* bits, int n, int stride, float* scale_out, void* stream) {
+  if (!bits || !scale_out || n <= 0 || stride <= 0) return lwm_fail(LWM_ERR_ARG, "attn_scale_from_absmax: bad arguments");
+  if (!lwm_check_device()) return LWM_ERR_DEVICE;
+  scale_from_absmax_kernel<<<1, 1, 0, reinterpret_cast<cudaStream_t>(stream)>>>(bits, n, stride, scale_out);
+  return lwm_check_launch("scale_from_absmax_kernel");
+}
+
+extern "C" int lwm_attn_to_f16_scaled(const void* x, int dtype, void* dst_f16, const float* scale, long long n, void* stream) {
+  if (!x || !dst_f16 || !scale || n <= 0 || n % 8 || (dtype != 0 && dtype != 1)) return lwm_fail(LWM_ERR_ARG, "attn_to_f16_scaled: bad arguments (n % 8 == 0)");
+  if (!lwm_check_device()) return LWM_ERR_DEVICE;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (dtype == 1)
+    bf16_to_f16_by_scale_kernel<<<grid_for(n / 8, 256, 8), 256, 0, st>>>(reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(dst_f16), n / 8, scale);
+  else
+    f32_to_f16_by_scale_kernel<<<grid_for(n / 4, 256, 8), 256, 0, st>>>(reinterpret_cast<const float4*>(x), reinterpret_cast<uint2*>(dst_f16), n / 4, scale);
+  return lwm_check_launch("to_f16_by_scale kernel");
+}
+
+extern "C" int lwm_attn_bwd_prep_f16(const void* out, int out_dtype, const void* dout16, const float* scale_do, float* delta,
+                                     int B, int H, int Sq, int D, void* stream) {
+  if (D != kHeadDim) return lwm_fail(LWM_ERR_SHAPE, "attn_bwd_prep_f16: head_dim must be 128");
+  if (!out || !dout16 || !scale_do || !delta || (out_dtype != 0 && out_dtype != 1)) return lwm_fail(LWM_ERR_ARG, "attn_bwd_prep_f16: bad arguments");
+  if (!lwm_check_device()) return LWM_ERR_DEVICE;
+  const long long rows = (long long)B * Sq * H;
+  const int warps = 8;
+  const unsigned blocks = unsigned((rows + warps - 1) / warps);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (out_dtype == 0) bwd_prep_f16_kernel<true><<<blocks, warps * 32, 0, st>>>(out, reinterpret_cast<const __half*>(dout16), scale_do, delta, B, H, Sq);
+  else bwd_prep_f16_kernel<false><<<blocks, warps * 32, 0, st>>>(out, reinterpret_cast<const __half*>(dout16), scale_do, delta, B, H, Sq);
+  return lwm_check_launch("bwd_prep_f16_kernel");
+}
+
+// host_srcs: HOST array of n_src device pointers (fp32, n elements each); dst_dtype 0 = fp32, 1 = bf16.
+extern "C" int lwm_reduce_cast_f32(const float* const* host_srcs, int n_src, void* dst, int dst_dtype, long long n, void* stream) {
+  if (!host_srcs || !dst || n_src < 1 || n_src > LWM_REDUCE_MAX_SRCS || n <= 0 || n % 4 || (dst_dtype != 0 && dst_dtype != 1))
+    return lwm_fail(LWM_ERR_ARG, "reduce_cast_f32: bad arguments (1..16 sources, n % 4 == 0)");
+  if (!lwm_check_device()) return LWM_ERR_DEVICE;
+  ReduceSrcs rs;
+  for (int i = 0; i < LWM_REDUCE_MAX_SRCS; ++i) rs.p[i] = reinterpret_cast<const float4*>(host_srcs[i < n_src ? i : 0]);
+  for (int i = 0; i < n_src; ++i)
+    if (!host_srcs[i]) return lwm_fail(LWM_ERR_ARG, "reduce_cast_f32: null source");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (dst_dtype == 1) reduce_cast_kernel<true><<<grid_for(n / 4, 256, 16), 256, 0, st>>>(rs, n_src, dst, n / 4);
+  else reduce_cast_kernel<false><<<grid_for(n / 4, 256, 16), 256, 0, st>>>(rs, n_src, dst, n / 4);
+  return lwm_check_launch("reduce_cast_kernel");
 }

@@ -1,0 +1,457 @@
+"""Peer-memory executor of the sequence-parallel attention op — the default multi-GPU path.
+
+What the reference does with `lax.ppermute(k, v)` hop by hop (un-vendored `ringattention` package, entered at
+lwm/llama.py:539-569) is done here the NVSwitch way: every rank STAGES its K/V (and Q or dO) once
+per pass in a heap all peers map (include/lwm_b200.h: lwm_ring_ctx_*), every rank PULLS the chunks it needs with
+copy-engine transfers (no SMs, no matching call on the owner) into a position-ordered local copy of K/V, and runs the
+tile kernels over whatever contiguous range has arrived. Results that belong to another rank — O / dQ chunks of the
+zigzag work assignment, dK/dV partials — are PUT into landing slots of the owner's heap. All ordering is done with
+32-bit flags in the heaps (remote flag write behind the payload on the same stream; cuStreamWaitValue32 on the local
+flag): there is no host synchronisation and no two-sided rendezvous anywhere on the data path.
+
+Protocol of one pass (forward or backward; `pid` = pass counter, identical on all ranks; `set` = pid & 1 selects one of
+two copies of every heap region, so a rank may start pass n+1 while slower peers still read its pass-n data):
+  1. (fp16 operand mode) |max| of the local shards -> every peer's table, flag ABS[rank] = pid; wait ABS[*]; all
+     ranks derive the same power-of-two scales.
+  2. stage K, V (own rows of the position-ordered K/V arrays) and Q (forward) / dO (backward); flag STAGED[rank] = pid
+     on every peer.
+  3. pull stream: wait STAGED[owner] once per owner, then one copy per (K|V chunk); one event per group of chunks.
+  4. main stream: per group, wait for its event, launch the tile kernels (carries merged in the kernels' epilogues).
+  5. push stream (backward): after a remote chunk's launches, put its fp32 dK/dV partial into the owner's landing slot,
+     flag PART[slot] = pid. Exit: put O / dQ chunks computed for other ranks, flag RES[rank] = pid.
+  6. owner: wait PART[*] / RES[*], fold partials (one fused sum + cast pass), copy landed chunks into the outputs.
+Heap reuse is safe without an end-of-pass barrier: a rank signals STAGED(pid) only after everything of its pass pid-1
+has been enqueued before it on the same stream, every rank waits for all peers' STAGED(pid) during pass pid, and pass
+pid+1 touches the other region set.
+
+The transport (`tr`) and the step functions (`ops`) are injected: tests/peer_emulation.py runs this very file on CPU
+with shared-memory heaps and oracle-backed step functions (tests/test_ring_peer_cpu.py).
+"""
+import ctypes
+import os
+
+import torch
+import torch.distributed as dist
+
+from . import _lib
+from . import ring_schedule as rs
+
+FLAG_ABS, FLAG_STAGED, FLAG_RES, FLAG_PART = 0, 16, 32, 64
+_ALIGN = 256
+
+
+def _al(n):
+    return (n + _ALIGN - 1) // _ALIGN * _ALIGN
+
+
+class Layout:
+    """Byte offsets inside every rank's heap payload — a pure function of the GLOBAL call shape, so a rank can address
+    any region of any peer. Two sets (pass parity) of: |max| table, K array, V array (position-ordered, [B, P*Sk, H, D]),
+    Q/dO stage [B, Sq, H, D], two landing areas for O/dQ rows computed elsewhere (4-byte and 2-byte elements) and the
+    dK/dV partial landing slots (chunks_per_rank * world slots of one chunk, dK then dV, fp32)."""
+
+    def __init__(self, B, Sq, Sk, H, D, world, chunks_per_rank, op_itemsize):
+        row = H * D
+        self.B, self.Sq, self.Sk, self.row, self.world, self.isz = B, Sq, Sk, row, world, op_itemsize
+        self.chunk_rows = Sk // chunks_per_rank
+        self.n_slots = chunks_per_rank * world
+        off = 0
+        self.abs = off; off += _al(world * 16)
+        self.kg = off; off += _al(B * world * Sk * row * op_itemsize)
+        self.vg = off; off += _al(B * world * Sk * row * op_itemsize)
+        self.qs = off; off += _al(B * Sq * row * op_itemsize)
+        self.lq4 = off; off += _al(B * Sq * row * 4)
+        self.lq2 = off; off += _al(B * Sq * row * 2)
+        self.slot_bytes = _al(B * self.chunk_rows * row * 4)
+        self.lp = off; off += self.n_slots * 2 * self.slot_bytes
+        self.set_bytes = off
+        self.total = 2 * off
+
+    def base(self, which):
+        return which * self.set_bytes
+
+    def kv_row_off(self, region, which, b, pos):
+        """byte offset of global key row `pos` of batch b in the K (region='kg') or V array"""
+        return self.base(which) + getattr(self, region) + (b * self.world * self.Sk + pos) * self.row * self.isz
+
+    def q_row_off(self, region, which, b, row, itemsize):
+        return self.base(which) + getattr(self, region) + (b * self.Sq + row) * self.row * itemsize
+
+    def slot_off(self, which, slot, tensor):
+        return self.base(which) + self.lp + (slot * 2 + tensor) * self.slot_bytes
+
+
+# ------------------------------------------------------------------------------------------------
+# CUDA transport over the C-ABI ring context
+# ------------------------------------------------------------------------------------------------
+class _RawCuda:
+    def __init__(self, addr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (addr, False), "version": 2}
+
+
+class CudaPeerTransport:
+    """One per (process group, device). Owns the lwm_ring_ctx, two side streams and the pass counter."""
+    _instances = {}
+
+    @classmethod
+    def get(cls, group, device):
+        key = (id(group) if group is not None else 0, device.index)
+        if key not in cls._instances:
+            cls._instances[key] = cls(group, device)
+        return cls._instances[key]
+
+    def __init__(self, group, device):
+        self.group, self.device = group, device
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.ctx, self.capacity, self.pass_id = None, 0, 0
+        self.heap_addr, self.own = [], None
+        self.signal_mode = int(os.environ.get("LWM_RING_SIGNAL", "0"))
+        self.side = {"pull": torch.cuda.Stream(device=device), "push": torch.cuda.Stream(device=device)}
+
+    def ensure(self, nbytes):
+        """(Re)create the heap collectively when the call needs more than is mapped. Every rank sees the same sizes
+        (the layout is a function of the global shape), so all of them take this branch together."""
+        if self.ctx is not None and nbytes <= self.capacity:
+            return
+        torch.cuda.synchronize(self.device)
+        if self.ctx is not None:
+            dist.barrier(group=self.group)
+            _lib.call("lwm_ring_ctx_destroy", self.ctx)
+            self.ctx = None
+        want = int(nbytes * 1.05) + (1 << 20)
+        lib = _lib.load()
+        ctx = ctypes.c_void_p()
+        _lib.call("lwm_ring_ctx_create", self.rank, self.world, want, self.signal_mode, ctypes.byref(ctx))
+        handle = (ctypes.c_ubyte * 64)()
+        _lib.call("lwm_ring_ctx_get_handle", ctx, handle)
+        mine = torch.tensor(list(handle), dtype=torch.uint8, device=self.device)
+        allh = torch.empty(self.world * 64, dtype=torch.uint8, device=self.device)
+        dist.all_gather_into_tensor(allh, mine, group=self.group)
+        buf = (ctypes.c_ubyte * (self.world * 64))(*allh.cpu().tolist())
+        _lib.call("lwm_ring_ctx_open_peers", ctx, buf)
+        self.ctx, self.capacity, self.pass_id = ctx, want, 0
+        self.heap_addr = [int(lib.lwm_ring_ctx_heap(ctx, p)) for p in range(self.world)]
+        self.own = torch.as_tensor(_RawCuda(self.heap_addr[self.rank], want), device=self.device)
+        dist.barrier(group=self.group)      # nobody signals into a heap that is not mapped yet
+
+    def next_pass(self):
+        self.pass_id += 1
+        return self.pass_id
+
+    def heap_view(self, off, shape, dtype):
+        n = 1
+        for s in shape:
+            n *= s
+        nb = n * torch.empty((), dtype=dtype).element_size()
+        return self.own[off:off + nb].view(dtype).view(*shape)
+
+    def _stream(self, name):
+        return torch.cuda.current_stream(self.device) if name == "main" else self.side[name]
+
+    def _sp(self, name):
+        return ctypes.c_void_p(self._stream(name).cuda_stream)
+
+    def pull(self, dst, peer, off, stream):
+        assert dst.is_contiguous()
+        _lib.call("lwm_ring_copy", ctypes.c_void_p(dst.data_ptr()), ctypes.c_void_p(self.heap_addr[peer] + off),
+                  dst.numel() * dst.element_size(), self._sp(stream))
+
+    def put(self, src, peer, off, stream):
+        assert src.is_contiguous()
+        _lib.call("lwm_ring_copy", ctypes.c_void_p(self.heap_addr[peer] + off), ctypes.c_void_p(src.data_ptr()),
+                  src.numel() * src.element_size(), self._sp(stream))
+
+    def signal(self, peer, flag, value, stream):
+        _lib.call("lwm_ring_signal", self.ctx, peer, flag, value, self._sp(stream))
+
+    def wait(self, flag, value, stream):
+        _lib.call("lwm_ring_wait", self.ctx, flag, value, self._sp(stream))
+
+    def record(self, stream):
+        return self._stream(stream).record_event()
+
+    def wait_event(self, stream, event):
+        self._stream(stream).wait_event(event)
+
+    def on(self, stream):
+        return torch.cuda.stream(self._stream(stream))
+
+
+# ------------------------------------------------------------------------------------------------
+# executor
+# ------------------------------------------------------------------------------------------------
+def _layout_for(plan, q_shape, Sk, ops):
+    B, Sq, H, D = q_shape
+    return Layout(B, Sq, Sk, H, D, plan.world, plan.chunks_per_rank, ops.op_itemsize)
+
+
+def _exchange_scales(tr, lay, which, pid, ops, tensors):
+    """tensors: {column: local tensor}. Every rank contributes the |max| bit pattern of its shard; returns
+    {column: device float scale} — identical on all ranks (None when the ops do not scale)."""
+    if not ops.scaled:
+        return {c: None for c in tensors}
+    P, r = tr.world, tr.rank
+    table = tr.heap_view(lay.base(which) + lay.abs, (P, 4), torch.int32)
+    table[r].zero_()
+    for c, t in tensors.items():
+        ops.absmax(t, table[r, c:c + 1])
+    for p in range(P):
+        if p != r:
+            tr.put(table[r], p, lay.base(which) + lay.abs + r * 16, "main")
+            tr.signal(p, FLAG_ABS + r, pid, "main")
+    for p in range(P):
+        if p != r:
+            tr.wait(FLAG_ABS + p, pid, "main")
+    return {c: ops.make_scale(table, c) for c in tensors}
+
+
+def _stage_and_announce(tr, lay, which, pid, ops, k, v, x, scales):
+    """K/V -> own rows of the position-ordered arrays, x (Q or dO) -> the stage; then STAGED[rank] = pid everywhere."""
+    P, r = tr.world, tr.rank
+    B, Sk = k.shape[0], k.shape[1]
+    KG = tr.heap_view(lay.base(which) + lay.kg, (B, P * Sk) + tuple(k.shape[2:]), ops.op_dtype)
+    VG = tr.heap_view(lay.base(which) + lay.vg, (B, P * Sk) + tuple(k.shape[2:]), ops.op_dtype)
+    QS = tr.heap_view(lay.base(which) + lay.qs, tuple(x.shape), ops.op_dtype)
+    for b in range(B):
+        ops.stage(k[b], KG[b, r * Sk:(r + 1) * Sk], scales[0])
+        ops.stage(v[b], VG[b, r * Sk:(r + 1) * Sk], scales[1])
+    ops.stage(x, QS, scales[2])
+    for p in range(P):
+        if p != r:
+            tr.signal(p, FLAG_STAGED + r, pid, "main")
+    return KG, VG, QS
+
+
+def _close_pass(tr, pid):
+    """Every rank has seen every peer ENTER pass pid before it leaves it. A peer signals STAGED(pid) only after its
+    whole pass pid-1 (pulls from my heap, consumption of what I put into its heap) was enqueued before it, so when I
+    overwrite this parity's regions again in pass pid+1 ... pid+2 nobody can still be reading them. Costs nothing:
+    by the end of a pass the peers have long staged."""
+    for p in range(tr.world):
+        if p != tr.rank:
+            tr.wait(FLAG_STAGED + p, pid, "main")
+
+
+class _OwnerGate:
+    """wait for STAGED[owner] once per (stream, owner)"""
+
+    def __init__(self, tr, pid):
+        self.tr, self.pid, self.seen = tr, pid, set()
+
+    def __call__(self, owner, stream):
+        if owner != self.tr.rank and (stream, owner) not in self.seen:
+            self.tr.wait(FLAG_STAGED + owner, self.pid, stream)
+            self.seen.add((stream, owner))
+
+
+def _gather_q_chunks(tr, lay, which, plan, QS, gate, ops):
+    """-> this rank's compute chunks of the staged Q-like tensor (views of the local stage or pulled copies)"""
+    B = QS.shape[0]
+    chunks = []
+    for qc in plan.q_chunks:
+        if qc.owner == tr.rank:
+            chunks.append(QS[:, qc.start:qc.start + qc.length])
+        else:
+            buf = torch.empty((B, qc.length) + tuple(QS.shape[2:]), dtype=QS.dtype, device=QS.device)
+            gate(qc.owner, "pull")
+            for b in range(B):
+                tr.pull(buf[b], qc.owner, lay.q_row_off("qs", which, b, qc.start, lay.isz), "pull")
+            chunks.append(buf)
+    return chunks
+
+
+def _pull_group(tr, lay, which, group, KG, VG, gate):
+    B = KG.shape[0]
+    for c in group.chunks:
+        if c.owner == tr.rank:
+            continue
+        gate(c.owner, "pull")
+        for b in range(B):
+            for region, arr in (("kg", KG), ("vg", VG)):
+                tr.pull(arr[b, c.pos0:c.pos0 + c.length], c.owner, lay.kv_row_off(region, which, b, c.pos0), "pull")
+    return tr.record("pull")
+
+
+def _return_rows(tr, lay, which, pid, plan, chunks, out, region, itemsize):
+    """Exit permutation: rows computed here for other ranks go to the owner's landing area, mine come back the same way.
+    chunks[i] belongs to plan.q_chunks[i]; `out` [B, Sq, H, D] is this rank's contiguous result."""
+    B, r = out.shape[0], tr.rank
+    ev = tr.record("main")
+    tr.wait_event("push", ev)
+    dests = set()
+    for qc, c in zip(plan.q_chunks, chunks):
+        if qc.owner == r:
+            out[:, qc.start:qc.start + qc.length].copy_(c)
+        else:
+            for b in range(B):
+                tr.put(c[b], qc.owner, lay.q_row_off(region, which, b, qc.start, itemsize), "push")
+            dests.add(qc.owner)
+    for p in sorted(dests):
+        tr.signal(p, FLAG_RES + r, pid, "push")
+    land = tr.heap_view(lay.base(which) + getattr(lay, region), tuple(out.shape), out.dtype)
+    for peer in sorted({peer for (_, _, peer) in plan.q_sends}):
+        tr.wait(FLAG_RES + peer, pid, "main")
+    for (s, l, peer) in plan.q_sends:
+        out[:, s:s + l].copy_(land[:, s:s + l])
+    return out
+
+
+def run_forward(plan, q, k, v, bias, seg, causal, ops, tr, want_f32=False):
+    """-> (out [B,Sq,H,D] in bf16 or fp32, residuals). q/k/v: bf16 or fp32 shards (contiguous sharding)."""
+    B, Sq, H, D = q.shape
+    Sk = k.shape[1]
+    dev = q.device
+    lay = _layout_for(plan, q.shape, Sk, ops)
+    tr.ensure(lay.total)
+    pid = tr.next_pass()
+    which = pid & 1
+    tr.wait_event("pull", tr.record("main"))            # this set's previous consumers (pass pid-2) are done
+    sc = _exchange_scales(tr, lay, which, pid, ops, {0: q, 1: k, 2: v})
+    KG, VG, QS = _stage_and_announce(tr, lay, which, pid, ops, k, v, q, (sc[1], sc[2], sc[0]))
+    tr.wait_event("pull", tr.record("main"))
+    gate = _OwnerGate(tr, pid)
+    q_chunks = _gather_q_chunks(tr, lay, which, plan, QS, gate, ops)
+    ev_q = tr.record("pull")
+    events = [_pull_group(tr, lay, which, g, KG, VG, gate) for g in plan.fwd_groups]
+
+    n_q = len(q_chunks)
+    n_launch = [sum(1 for g in plan.fwd_groups for (qi, _, _) in g.launches if qi == i) for i in range(n_q)]
+    out_chunks = [torch.empty((B, c.shape[1], H, D), dtype=torch.bfloat16, device=dev) for c in q_chunks]
+    need32 = want_f32 or ops.scaled     # fp16 mode keeps the un-rounded output as the backward's residual
+    out32 = [torch.empty((B, c.shape[1], H, D), dtype=torch.float32, device=dev) if need32 else None for c in q_chunks]
+    lse_chunks = [torch.empty((B, H, c.shape[1]), dtype=torch.float32, device=dev) for c in q_chunks]
+    acc = [None] * n_q
+    for i in range(n_q):
+        if n_launch[i] > 1:
+            L = q_chunks[i].shape[1]
+            acc[i] = (torch.empty((B, L, H, D), dtype=torch.float32, device=dev),
+                      torch.empty((B, H, L), dtype=torch.float32, device=dev),
+                      torch.empty((B, H, L), dtype=torch.float32, device=dev))
+    done = [0] * n_q
+    tr.wait_event("main", ev_q)
+    scales = (sc[0], sc[1], sc[2])
+    for g, ev in zip(plan.fwd_groups, events):
+        tr.wait_event("main", ev)
+        for (qi, p0, rows) in g.launches:
+            first, last = done[qi] == 0, done[qi] == n_launch[qi] - 1
+            done[qi] += 1
+            a = acc[qi] or (None, None, None)
+            for b in range(B):
+                sl = slice(b, b + 1)
+                ops.fwd_step(q_chunks[qi][sl], KG[sl, p0:p0 + rows], VG[sl, p0:p0 + rows], out_chunks[qi][sl],
+                             lse_chunks[qi][sl], None if a[0] is None else a[0][sl], None if a[1] is None else a[1][sl],
+                             None if a[2] is None else a[2][sl], plan.q_chunks[qi].pos0, p0, causal,
+                             None if bias is None else bias[sl], None if seg is None else seg[sl], first, last, scales,
+                             None if out32[qi] is None else out32[qi][sl])
+    for i in range(n_q):
+        if n_launch[i] == 0:     # a chunk that sees no key at all cannot occur with Sq == Sk causal; keep it defined
+            out_chunks[i].zero_()
+            lse_chunks[i].fill_(float("-inf"))
+            if out32[i] is not None:
+                out32[i].zero_()
+    if want_f32:
+        out = _return_rows(tr, lay, which, pid, plan, out32, torch.empty((B, Sq, H, D), dtype=torch.float32, device=dev),
+                           "lq4", 4)
+    else:
+        out = _return_rows(tr, lay, which, pid, plan, out_chunks, torch.empty((B, Sq, H, D), dtype=torch.bfloat16, device=dev),
+                           "lq2", 2)
+    tr.wait_event("main", tr.record("push"))
+    _close_pass(tr, pid)
+    # the local Q chunk is a view of the heap stage, which the next pass of this parity overwrites: keep a copy
+    q_res = [c.clone() if qc.owner == tr.rank else c for qc, c in zip(plan.q_chunks, q_chunks)]
+    res = dict(q_chunks=q_res, out_chunks=[o32 if ops.scaled else ob for o32, ob in zip(out32, out_chunks)],
+               lse_chunks=lse_chunks, scales=scales)
+    return out, res
+
+
+def run_backward(plan, res, k, v, dout, bias, seg, causal, ops, tr, want_f32=False):
+    """-> dq, dk, dv (contiguous shards; bf16, or fp32 when want_f32). `res`: residuals of run_forward."""
+    B, Sk, H, D = k.shape
+    Sq = dout.shape[1]
+    dev = k.device
+    P, r = tr.world, tr.rank
+    lay = _layout_for(plan, dout.shape, Sk, ops)
+    tr.ensure(lay.total)
+    pid = tr.next_pass()
+    which = pid & 1
+    tr.wait_event("pull", tr.record("main"))
+    tr.wait_event("push", tr.record("main"))
+    sq, sk, sv = res["scales"]
+    sdo = _exchange_scales(tr, lay, which, pid, ops, {3: dout})[3]
+    KG, VG, DS = _stage_and_announce(tr, lay, which, pid, ops, k, v, dout, (sk, sv, sdo))
+    tr.wait_event("pull", tr.record("main"))
+    gate = _OwnerGate(tr, pid)
+    do_chunks = _gather_q_chunks(tr, lay, which, plan, DS, gate, ops)
+    ev_q = tr.record("pull")
+    events = [_pull_group(tr, lay, which, g, KG, VG, gate) for g in plan.bwd_groups]
+
+    q_chunks, out_chunks, lse_chunks = res["q_chunks"], res["out_chunks"], res["lse_chunks"]
+    n_q = len(q_chunks)
+    tr.wait_event("main", ev_q)
+    delta = [torch.empty_like(l) for l in lse_chunks]
+    for i in range(n_q):
+        ops.bwd_prep(out_chunks[i], do_chunks[i], sdo, delta[i])
+    nlse = [ops.lse_for_bwd(l) for l in lse_chunks]
+    dq_acc = [torch.zeros((B, c.shape[1], H, D), dtype=torch.float32, device=dev) for c in q_chunks]
+    # position-ordered fp32 accumulators; every chunk's rows are initialised by its first launch (dkv_init)
+    dKG = torch.empty((B, P * Sk, H, D), dtype=torch.float32, device=dev)
+    dVG = torch.empty((B, P * Sk, H, D), dtype=torch.float32, device=dev)
+    scales = (sq, sk, sv, sdo)
+    for g, ev in zip(plan.bwd_groups, events):
+        tr.wait_event("main", ev)
+        seen = set()
+        for (qi, p0, rows) in g.launches:
+            init = p0 not in seen
+            seen.add(p0)
+            for b in range(B):
+                sl = slice(b, b + 1)
+                ops.bwd_step(q_chunks[qi][sl], KG[sl, p0:p0 + rows], VG[sl, p0:p0 + rows], do_chunks[qi][sl],
+                             nlse[qi][sl], delta[qi][sl], dq_acc[qi][sl], dKG[sl, p0:p0 + rows], dVG[sl, p0:p0 + rows],
+                             plan.q_chunks[qi].pos0, p0, causal, None if bias is None else bias[sl],
+                             None if seg is None else seg[sl], scales, init)
+        c = g.chunks[0]
+        if c.owner != r and g.launches:
+            tr.wait_event("push", tr.record("main"))
+            slot = plan.slot(c.index, r)
+            for t, arr in enumerate((dKG, dVG)):
+                for b in range(B):
+                    tr.put(arr[b, c.pos0:c.pos0 + c.length], c.owner,
+                           lay.slot_off(which, slot, t) + b * c.length * lay.row * 4, "push")
+            tr.signal(c.owner, FLAG_PART + slot, pid, "push")
+
+    # dQ: cast and return to the rows' owners
+    res_dtype = torch.float32 if want_f32 else torch.bfloat16
+    if want_f32:
+        dq_chunks = dq_acc
+    else:
+        dq_chunks = []
+        for i in range(n_q):
+            c = torch.empty(dq_acc[i].shape, dtype=torch.bfloat16, device=dev)
+            ops.cast(dq_acc[i], c)
+            dq_chunks.append(c)
+    dq = _return_rows(tr, lay, which, pid, plan, dq_chunks, torch.empty((B, Sq, H, D), dtype=res_dtype, device=dev),
+                      "lq4" if want_f32 else "lq2", 4 if want_f32 else 2)
+    # dK/dV: own partial + landed partials -> one fused sum + cast per chunk
+    dk = torch.empty((B, Sk, H, D), dtype=res_dtype, device=dev)
+    dv = torch.empty((B, Sk, H, D), dtype=res_dtype, device=dev)
+    for (ci, peer) in plan.incoming:
+        tr.wait(FLAG_PART + plan.slot(ci, peer), pid, "main")
+    L = lay.chunk_rows
+    for ci in range(plan.chunks_per_rank):
+        for t, (acc_g, dst) in enumerate(((dKG, dk), (dVG, dv))):
+            for b in range(B):
+                srcs = []
+                if ci in plan.own_computed:
+                    srcs.append(acc_g[b, r * Sk + ci * L:r * Sk + (ci + 1) * L])
+                for (cj, peer) in plan.incoming:
+                    if cj == ci:
+                        off = lay.slot_off(which, plan.slot(ci, peer), t) + b * L * lay.row * 4
+                        srcs.append(tr.heap_view(off, (L, H, D), torch.float32))
+                if srcs:
+                    ops.reduce_cast(srcs, dst[b, ci * L:(ci + 1) * L])
+                else:
+                    dst[b, ci * L:(ci + 1) * L].zero_()
+    tr.wait_event("main", tr.record("push"))
+    tr.wait_event("main", tr.record("pull"))
+    _close_pass(tr, pid)
+    return dq, dk, dv

@@ -152,24 +152,6 @@ def make_plan(world, rank, Sq, Sk, causal, layout="auto", n_sub_first=1, n_sub_l
     return Plan(world, rank, layout, q_chunks, q_sends, steps, (Sq, Sk, causal, n_sub_first, n_sub_last))
 
 
-def peer_plan(plan, peer):
-    """The plan rank `peer` derives for the same call (plans are pure functions of the call's shape)."""
-    Sq, Sk, causal, n_first, n_last = plan.params
-    return make_plan(plan.world, peer, Sq, Sk, causal, plan.layout, n_first, n_last)
-
-
-def landing_slots(plan):
-    """One-sided dK/dV return: every block of MY shard that a peer fetches at some step comes back as one fp32
-    partial (dk, dv). Slots are laid out in plan order -> {(step, peer, start, length): row offset} and the total
-    number of rows; a sender finds its slot with landing_slots(peer_plan(plan, owner))."""
-    table, rows = {}, 0
-    for idx, st in enumerate(plan.steps):
-        for (s, l, peer) in st.sends:
-            table[(idx, peer, s, l)] = rows
-            rows += l
-    return table, rows
-
-
 def work_units(plan, causal):
     """Causal work (in units of full chunk x chunk tiles; a diagonal pair counts 1/2) per step —
     used by the tests to assert the balance property of the zigzag schedule."""
@@ -184,3 +166,116 @@ def work_units(plan, causal):
                 w += 1.0 * qc.length * kv.length
         out.append(w)
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# Peer-memory schedule (ring_peer.py): no lock-step ring — every rank pulls the K/V chunks it needs
+# straight out of their owners' heaps, in a rank-staggered ("ring") order so that every owner serves
+# about one puller at a time, and processes them in groups.
+# ------------------------------------------------------------------------------------------------
+@dataclass
+class Chunk:
+    owner: int      # rank holding the rows (contiguous sharding)
+    index: int      # which of the owner's chunks (0 .. chunks_per_rank-1)
+    start: int      # row offset inside the owner's shard
+    length: int
+    pos0: int       # global token position of the first row
+
+
+@dataclass
+class Group:
+    chunks: List[Chunk] = field(default_factory=list)          # K/V chunks that must have arrived
+    launches: List[Tuple[int, int, int]] = field(default_factory=list)   # (q chunk idx, first global key row, rows)
+
+
+@dataclass
+class PeerPlan:
+    world: int
+    rank: int
+    layout: str
+    chunks_per_rank: int
+    q_chunks: List[QRef]                      # query chunks this rank computes (references into the owners' shards)
+    q_sends: List[Tuple[int, int, int]]       # (start, length, peer): rows of MY shard that `peer` computes
+    fwd_groups: List[Group]                   # coarse groups (few launches, few carry round trips)
+    bwd_groups: List[Group]                   # one K/V chunk per launch (dK/dV partials leave chunk by chunk)
+    incoming: List[Tuple[int, int]]           # (my chunk index, peer): dK/dV partials that will land in my heap
+    own_computed: List[int]                   # my chunk indices I compute a partial for myself
+
+    def slot(self, chunk_index, peer):
+        """landing slot (in the OWNER's heap) of the partial `peer` computes for the owner's chunk `chunk_index`"""
+        return chunk_index * self.world + peer
+
+
+def kv_chunks_of(world, rank, Sk, layout):
+    """the chunks rank `rank` OWNS (contiguous sharding): one per rank, or two half-shards under zigzag"""
+    if layout == "contiguous":
+        return [Chunk(rank, 0, 0, Sk, rank * Sk)]
+    h = Sk // 2
+    return [Chunk(rank, 0, 0, h, rank * Sk), Chunk(rank, 1, h, h, rank * Sk + h)]
+
+
+def _merge_ranges(chunks):
+    """contiguous global-position ranges [(pos0, rows)] covered by `chunks`"""
+    out = []
+    for c in sorted(chunks, key=lambda c: c.pos0):
+        if out and out[-1][0] + out[-1][1] == c.pos0:
+            out[-1] = (out[-1][0], out[-1][1] + c.length)
+        else:
+            out.append((c.pos0, c.length))
+    return out
+
+
+def make_peer_plan(world, rank, Sq, Sk, causal, layout="auto", fwd_group_chunks=4):
+    layout = choose_layout(world, Sq, Sk, causal, layout)
+    q_chunks = compute_chunks(world, rank, Sq, layout)
+    q_sends = []
+    for peer in range(world):
+        if peer != rank:
+            q_sends += [(qc.start, qc.length, peer) for qc in compute_chunks(world, peer, Sq, layout) if qc.owner == rank]
+
+    def sees(qc, c):
+        return visible(qc.pos0, qc.length, c.pos0, causal)
+
+    def needed_by(r):
+        qs = compute_chunks(world, r, Sq, layout)
+        return [c for o in range(world) for c in kv_chunks_of(world, o, Sk, layout) if any(sees(qc, c) for qc in qs)]
+
+    need = needed_by(rank)
+    local = [c for c in need if c.owner == rank]
+    # ring order: owners rank-1, rank-2, ... (every owner then serves ~one puller at a time)
+    remote = []
+    for d in range(1, world):
+        o = (rank - d) % world
+        remote += [c for c in need if c.owner == o]
+
+    def launches_for(chunks):
+        ls = []
+        for qi, qc in enumerate(q_chunks):
+            for (p0, rows) in _merge_ranges([c for c in chunks if sees(qc, c)]):
+                ls.append((qi, p0, rows))
+        return ls
+
+    # forward: local chunks first (their compute hides the first pulls), then the remote chunks in a few big groups
+    fwd_groups = []
+    if local:
+        fwd_groups.append(Group(local, launches_for(local)))
+    first = 1 if not local else fwd_group_chunks
+    i = 0
+    while i < len(remote):
+        n = first if i == 0 else fwd_group_chunks
+        g = remote[i:i + n]
+        fwd_groups.append(Group(g, launches_for(g)))
+        i += n
+    # backward: one chunk per launch; a local chunk first (hides the first pulls) and a local chunk last (hides the
+    # last partial's flight) when there are any
+    order = (local[:1] + remote + local[1:]) if local else remote
+    bwd_groups = []
+    for c in order:
+        bwd_groups.append(Group([c], [(qi, c.pos0, c.length) for qi, qc in enumerate(q_chunks) if sees(qc, c)]))
+    incoming = []
+    for c in kv_chunks_of(world, rank, Sk, layout):
+        for peer in range(world):
+            if peer != rank and any(n.owner == rank and n.index == c.index for n in needed_by(peer)):
+                incoming.append((c.index, peer))
+    return PeerPlan(world, rank, layout, 1 if layout == "contiguous" else 2, q_chunks, q_sends, fwd_groups, bwd_groups,
+                    incoming, [c.index for c in local])

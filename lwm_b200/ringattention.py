@@ -24,18 +24,18 @@ import torch.distributed as dist
 
 from . import _lib
 from . import ring_exec as rx
-from . import ring_exec_symm as rxs
+from . import ring_peer as rp
 from . import ring_schedule as rs
 
 _AXIS_GROUPS = {}
-_DEFAULT_PRECISION = os.environ.get("LWM_ATTN_PRECISION", "bf16")
+_DEFAULT_PRECISION = os.environ.get("LWM_ATTN_PRECISION", "fp16")
 
 
 def set_default_precision(precision: str) -> None:
-    """'bf16' (default): bf16 tensor-core operands, P/dS rounded to bf16 — the usual flash-attention numerics.
-    'fp16': every operand is converted once to an exact power-of-two-scaled fp16 copy and P/dS keep 11
-    significant bits — ~8x lower rounding noise (meets 1e-3 on white-noise inputs) for ~1 % extra time (measured:
-    profiles/precision_perf_r01.log)."""
+    """'fp16' (default — the mode that meets the 1e-3 parity bound): every operand is converted once per pass to a
+    power-of-two-scaled fp16 copy (exact for bf16 inputs, one rounding to 11 significant bits for fp32 inputs) and P / dS
+    keep fp16's 11 bits; un-rounded fp32 output kept as the backward's residual. 'bf16': bf16 tensor-core operands,
+    P / dS rounded to bf16 (8 bits) — the usual flash-attention numerics, 1.3e-3 .. 2.6e-3 on white-noise inputs."""
     global _DEFAULT_PRECISION
     if precision not in ("bf16", "fp16"):
         raise ValueError("precision must be 'bf16' or 'fp16'")
@@ -43,7 +43,8 @@ def set_default_precision(precision: str) -> None:
 
 
 def set_axis_group(axis_name: str, group) -> None:
-    """Bind a mesh-axis name (the reference's 'sp') to a torch.distributed process group."""
+    """Bind a mesh-axis name (the reference's 'sp') to a torch.distributed process group. Call it on every rank of
+    WORLD, in the same order, like torch.distributed.new_group itself."""
     _AXIS_GROUPS[axis_name] = group
 
 
@@ -106,10 +107,12 @@ class _RingAttnFn(torch.autograd.Function):
     def forward(ctx, q, k, v, bias, seg, causal, axis_name, layout, precision):
         group, rank, world = _resolve_group(axis_name)
         out, res = ring_forward(q, k, v, bias, seg, causal, group, rank, world, layout, precision)
-        # residuals stay in the schedule's compute layout (zigzag chunks), so the backward only has
+        # residuals stay in the schedule's compute layout (zigzag chunks, operand dtype), so the backward only has
         # to permute dout on entry and dq on exit
         ctx.n_chunks = len(res["q_chunks"])
-        ctx.save_for_backward(k, v, bias, seg, *res["q_chunks"], *res["out_chunks"], *res["lse_chunks"])
+        sc = [t for t in res.get("scales", ()) if t is not None]
+        ctx.n_scales = len(sc)
+        ctx.save_for_backward(k, v, bias, seg, *res["q_chunks"], *res["out_chunks"], *res["lse_chunks"], *sc)
         ctx.causal, ctx.axis_name, ctx.layout, ctx.precision = causal, axis_name, layout, precision
         return out
 
@@ -120,23 +123,39 @@ class _RingAttnFn(torch.autograd.Function):
         n = ctx.n_chunks
         res = dict(q_chunks=list(saved[4:4 + n]), out_chunks=list(saved[4 + n:4 + 2 * n]),
                    lse_chunks=list(saved[4 + 2 * n:4 + 3 * n]))
+        sc = list(saved[4 + 3 * n:4 + 3 * n + ctx.n_scales])
+        res["scales"] = tuple(sc) if sc else (None, None, None)
         group, rank, world = _resolve_group(ctx.axis_name)
         dq, dk, dv = ring_backward(res, k, v, dout.contiguous(), bias, seg, ctx.causal, group, rank, world,
                                    ctx.layout, ctx.precision)
         return dq, dk, dv, None, None, None, None, None, None
 
 
+def _check_mask_extent(bias, seg, rank, world, Sq, Sk):
+    """attn_bias / segment_ids are indexed by GLOBAL token position (they are replicated along the ring,
+    lwm/llama.py:563-564): a per-shard mask would be read out of bounds by the kernels."""
+    if bias is not None and bias.shape[-1] < world * Sk:
+        raise ValueError("attn_bias covers %d keys but the ring holds %d: pass the un-sharded [B,1,1,S_global] bias "
+                         "(lwm/llama.py:563)" % (bias.shape[-1], world * Sk))
+    if seg is not None and seg.shape[-1] < max(world * Sq, world * Sk):
+        raise ValueError("segment_ids covers %d positions but the ring holds %d: pass the un-sharded [B,S_global] ids "
+                         "(lwm/llama.py:564)" % (seg.shape[-1], max(world * Sq, world * Sk)))
+
+
 def ringattention(q, k, v, attn_bias=None, segment_ids=None, *, axis_name="sp", float32_logits=True,
                   cache_idx=None, blockwise_kwargs=None, layout="auto", precision=None):
-    """Drop-in for the reference op. q [B,Sq_loc,H,D], k/v [B,Sk_loc,H,D] bf16 CUDA shards of the
-    contiguously sequence-sharded tensors (in_specs lwm/llama.py:559-565); attn_bias
-    [B,1,1,S_global] additive (0 / finfo.min), segment_ids [B,S_global] or None, both replicated
-    along the ring. Returns the local output shard [B,Sq_loc,H,D]; differentiable w.r.t. q,k,v.
+    """Drop-in for the reference op. q [B,Sq_loc,H,D], k/v [B,Sk_loc,H,D] CUDA shards of the contiguously
+    sequence-sharded tensors (in_specs lwm/llama.py:559-565), all bfloat16 or all float32 (the dtype the reference's
+    scripts run with); attn_bias [B,1,1,S_global] additive (0 / finfo.min), segment_ids [B,S_global] or None, both
+    replicated along the ring. Returns the local output shard [B,Sq_loc,H,D] in the input dtype; differentiable w.r.t.
+    q,k,v (gradients in the input dtype). With float32 inputs in the default precision mode nothing is rounded to bf16:
+    the operands are rounded once to scaled fp16 (11 bits) and the output / gradients are the un-rounded fp32
+    accumulators.
 
     float32_logits: logits/softmax/carries are always fp32 here (the reference default, True).
     layout: 'contiguous' = the reference's schedule; 'zigzag' = internally rebalance the causal
     work across ranks (same inputs/outputs); 'auto' picks zigzag when it applies.
-    precision: None -> module default (set_default_precision / $LWM_ATTN_PRECISION): 'bf16' | 'fp16'."""
+    precision: None -> module default (set_default_precision / $LWM_ATTN_PRECISION): 'fp16' | 'bf16'."""
     precision = precision or _DEFAULT_PRECISION
     if precision not in ("bf16", "fp16"):
         raise ValueError("precision must be 'bf16' or 'fp16'")
@@ -145,22 +164,24 @@ def ringattention(q, k, v, attn_bias=None, segment_ids=None, *, axis_name="sp", 
     if not q.is_cuda:
         raise _lib.LwmError("ringattention: tensors must live on an sm_100 GPU (no CPU fallback)")
     in_dtype = q.dtype
-    if in_dtype == torch.float32 and k.dtype == torch.float32 and v.dtype == torch.float32:
-        # the reference's scripts run dtype='fp32'; the tensor cores take 16-bit operands, so fp32 callers go through
-        # one rounding of q/k/v to bf16 (2^-9 relative) and get the output / gradients back in fp32
-        q, k, v = q.to(torch.bfloat16), k.to(torch.bfloat16), v.to(torch.bfloat16)
-    if q.dtype != torch.bfloat16 or k.dtype != torch.bfloat16 or v.dtype != torch.bfloat16:
+    if not (k.dtype == in_dtype and v.dtype == in_dtype and in_dtype in (torch.bfloat16, torch.float32)):
         raise TypeError("ringattention: q, k, v must all be bfloat16 or all float32 (fp32 logits and accumulation "
                         "are internal)")
+    group, rank, world = _resolve_group(axis_name)
+    native_f32 = in_dtype == torch.float32 and precision == "fp16" and (world == 1 or _transport() == "peer")
+    if in_dtype == torch.float32 and not native_f32:
+        # bf16 operand mode / NCCL transport: fp32 callers go through one rounding of q/k/v to bf16 (2^-9 relative)
+        q, k, v = q.to(torch.bfloat16), k.to(torch.bfloat16), v.to(torch.bfloat16)
     B, Sq, H, D = q.shape
     causal = _check_blockwise_kwargs(blockwise_kwargs, Sq, k.shape[1])
     bias = _prep_bias(attn_bias, B)
     seg = None
     if segment_ids is not None:
         seg = segment_ids.to(torch.int32).contiguous()
+    _check_mask_extent(bias, seg, rank, world, Sq, k.shape[1])
     out = _RingAttnFn.apply(q.contiguous(), k.contiguous(), v.contiguous(), bias, seg, causal, axis_name, layout,
                             precision)
-    return out if in_dtype == torch.bfloat16 else out.to(in_dtype)
+    return out if out.dtype == in_dtype else out.to(in_dtype)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -213,8 +234,8 @@ def lse_for_bwd(lse, stream=None):
 
 
 def bwd_step(q, k, v, dout, lse, delta, dq_acc, dk_acc, dv_acc, q_pos0, k_pos0, causal, bias, seg, stream=None,
-             scales=None):
-    """`lse` is the PRE-SCALED array returned by lse_for_bwd."""
+             scales=None, init=False):
+    """`lse` is the PRE-SCALED array returned by lse_for_bwd. init=True: dk_acc/dv_acc rows are written, not accumulated."""
     B, Sq, H, D = q.shape
     Sk = k.shape[1]
     if scales is not None:   # (sq, sk, sv, sdo)
@@ -222,13 +243,13 @@ def bwd_step(q, k, v, dout, lse, delta, dq_acc, dk_acc, dv_acc, q_pos0, k_pos0, 
                   _lib.ptr(scales[1]), _lib.ptr(scales[2]), _lib.ptr(scales[3]), _lib.ptr(lse), _lib.ptr(delta),
                   _lib.ptr(dq_acc), _lib.ptr(dk_acc), _lib.ptr(dv_acc), B, H, Sq, Sk, D, int(q_pos0), int(k_pos0),
                   int(bool(causal)), _lib.ptr(bias), 0 if bias is None else bias.shape[1], _lib.ptr(seg),
-                  0 if seg is None else seg.shape[1], 1.0 / math.sqrt(D), _lib.stream_ptr(stream))
+                  0 if seg is None else seg.shape[1], 1.0 / math.sqrt(D), int(bool(init)), _lib.stream_ptr(stream))
         return
     _lib.call("lwm_attn_bwd_step", _lib.ptr(q), _lib.ptr(k), _lib.ptr(v), _lib.ptr(dout), _lib.ptr(lse),
               _lib.ptr(delta), _lib.ptr(dq_acc), _lib.ptr(dk_acc), _lib.ptr(dv_acc), B, H, Sq, Sk, D,
               int(q_pos0), int(k_pos0), int(bool(causal)), _lib.ptr(bias),
               0 if bias is None else bias.shape[1], _lib.ptr(seg), 0 if seg is None else seg.shape[1],
-              1.0 / math.sqrt(D), _lib.stream_ptr(stream))
+              1.0 / math.sqrt(D), int(bool(init)), _lib.stream_ptr(stream))
 
 
 def cast_f32_to_bf16(src, dst, stream=None):
@@ -292,12 +313,93 @@ def _f32_residuals(ops, res):
     return res
 
 
+# ------------------------------------------------------------------------------------------------
+# step functions in the form the peer-memory executor (ring_peer.py) and the single-GPU path take them
+# ------------------------------------------------------------------------------------------------
+def _dt(t):
+    if t.dtype == torch.float32:
+        return 0
+    if t.dtype == torch.bfloat16:
+        return 1
+    raise TypeError("expected float32 or bfloat16, got %s" % t.dtype)
+
+
+class PeerOpsF16:
+    """fp16 operand mode: operands are power-of-two-scaled fp16 copies sharing ONE scale per sharded tensor."""
+    op_dtype, op_itemsize, scaled = torch.float16, 2, True
+
+    @staticmethod
+    def absmax(x, bits):
+        _lib.call("lwm_attn_absmax", _lib.ptr(x), _dt(x), x.numel(), _lib.ptr(bits), _lib.stream_ptr())
+
+    @staticmethod
+    def make_scale(table, col):
+        s = torch.empty(1, dtype=torch.float32, device=table.device)
+        _lib.call("lwm_attn_scale_from_absmax", _lib.ptr(table.view(-1)[col:]), table.shape[0], table.shape[1],
+                  _lib.ptr(s), _lib.stream_ptr())
+        return s
+
+    @staticmethod
+    def stage(x, dst, scale):
+        _lib.call("lwm_attn_to_f16_scaled", _lib.ptr(x), _dt(x), _lib.ptr(dst), _lib.ptr(scale), x.numel(),
+                  _lib.stream_ptr())
+
+    @staticmethod
+    def fwd_step(q, k, v, out, lse, acc_o, acc_m, acc_l, q_pos0, k_pos0, causal, bias, seg, first, last, scales, out_f32):
+        fwd_step(q, k, v, out, lse, acc_o, acc_m, acc_l, q_pos0, k_pos0, causal, bias, seg, first, last, scales=scales,
+                 out_f32=out_f32)
+
+    @staticmethod
+    def bwd_prep(out, dout16, sdo, delta):
+        B, Sq, H, D = out.shape
+        _lib.call("lwm_attn_bwd_prep_f16", _lib.ptr(out), _dt(out), _lib.ptr(dout16), _lib.ptr(sdo), _lib.ptr(delta),
+                  B, H, Sq, D, _lib.stream_ptr())
+
+    lse_for_bwd = staticmethod(lse_for_bwd)
+
+    @staticmethod
+    def bwd_step(q, k, v, dout, lse, delta, dq_acc, dk_acc, dv_acc, q_pos0, k_pos0, causal, bias, seg, scales, init):
+        bwd_step(q, k, v, dout, lse, delta, dq_acc, dk_acc, dv_acc, q_pos0, k_pos0, causal, bias, seg, scales=scales,
+                 init=init)
+
+    @staticmethod
+    def reduce_cast(srcs, dst):
+        import ctypes
+        arr = (ctypes.c_void_p * len(srcs))(*[t.data_ptr() for t in srcs])
+        _lib.call("lwm_reduce_cast_f32", arr, len(srcs), _lib.ptr(dst), _dt(dst), dst.numel(), _lib.stream_ptr())
+
+    cast = staticmethod(cast_f32_to_bf16)
+
+
+class PeerOpsBf16(PeerOpsF16):
+    """bf16 operand mode: staging is a plain copy (fp32 inputs are rounded to bf16 there), no scales."""
+    op_dtype, op_itemsize, scaled = torch.bfloat16, 2, False
+
+    @staticmethod
+    def stage(x, dst, scale):
+        dst.copy_(x)
+
+    @staticmethod
+    def fwd_step(q, k, v, out, lse, acc_o, acc_m, acc_l, q_pos0, k_pos0, causal, bias, seg, first, last, scales, out_f32):
+        fwd_step(q, k, v, out, lse, acc_o, acc_m, acc_l, q_pos0, k_pos0, causal, bias, seg, first, last)
+        if last and out_f32 is not None:
+            out_f32.copy_(out)
+
+    @staticmethod
+    def bwd_prep(out, dout, sdo, delta):
+        bwd_prep(out, dout, delta)
+
+    @staticmethod
+    def bwd_step(q, k, v, dout, lse, delta, dq_acc, dk_acc, dv_acc, q_pos0, k_pos0, causal, bias, seg, scales, init):
+        bwd_step(q, k, v, dout, lse, delta, dq_acc, dk_acc, dv_acc, q_pos0, k_pos0, causal, bias, seg, init=init)
+
+
 def _transport():
-    """'nccl' (default, the measured path: ring_exec.py) | 'symm' (EXPERIMENTAL one-sided pulls/puts over torch symmetric
-    memory, ring_exec_symm.py — validated on CPU emulation only so far)."""
-    t = os.environ.get("LWM_RING_TRANSPORT", "nccl")
-    if t not in ("nccl", "symm"):
-        raise ValueError("LWM_RING_TRANSPORT must be 'nccl' or 'symm'")
+    """'peer' (default): copy-engine pulls/puts over peer-mapped heaps (ring_peer.py). 'nccl': the two-sided
+    send/recv executor (ring_exec.py) — kept as the portable alternative and for the gloo CPU tests."""
+    t = os.environ.get("LWM_RING_TRANSPORT", "peer")
+    if t not in ("nccl", "peer"):
+        raise ValueError("LWM_RING_TRANSPORT must be 'peer' or 'nccl'")
     return t
 
 
@@ -305,48 +407,90 @@ def _ops_for(precision):
     return CudaOpsF16() if precision == "fp16" else CudaOps
 
 
+def _peer_ops(precision):
+    return PeerOpsF16 if precision == "fp16" else PeerOpsBf16
+
+
+def _local_scales(ops, tensors):
+    """single GPU: per-tensor scales from the local |max| (same kernels as the sharded exchange, world = 1)"""
+    if not ops.scaled:
+        return [None] * len(tensors)
+    table = torch.zeros((1, 4), dtype=torch.int32, device=tensors[0].device)
+    out = []
+    for c, t in enumerate(tensors):
+        ops.absmax(t, table[0, c:c + 1])
+        out.append(ops.make_scale(table, c))
+    return out
+
+
+def _stage_local(ops, x, scale):
+    if not ops.scaled and x.dtype == ops.op_dtype:
+        return x
+    y = torch.empty(x.shape, dtype=ops.op_dtype, device=x.device)
+    ops.stage(x, y, scale)
+    return y
+
+
 def ring_forward(q, k, v, bias, seg, causal, group, rank, world, layout="auto", precision="bf16"):
-    """-> (out, residuals). world == 1 is the single-launch fast path (no carry buffers)."""
+    """-> (out, residuals). out is fp32 (un-rounded) for fp32 inputs, bf16 otherwise. world == 1 is the
+    single-launch path (no carry buffers)."""
     B, Sq, H, D = q.shape
-    ops = _ops_for(precision)
+    want_f32 = q.dtype == torch.float32
     if world == 1:
-        out = torch.empty_like(q)
+        ops = _peer_ops(precision)
+        sq, sk, sv = _local_scales(ops, (q, k, v))
+        q16, k16, v16 = _stage_local(ops, q, sq), _stage_local(ops, k, sk), _stage_local(ops, v, sv)
+        out = torch.empty((B, Sq, H, D), dtype=torch.bfloat16, device=q.device)
+        out32 = torch.empty((B, Sq, H, D), dtype=torch.float32, device=q.device) if (ops.scaled or want_f32) else None
         lse = torch.empty((B, H, Sq), dtype=torch.float32, device=q.device)
-        ops.fwd_step(q, k, v, out, lse, None, None, None, 0, 0, causal, bias, seg, True, True)
-        return out, _f32_residuals(ops, dict(q_chunks=[q], out_chunks=[out], lse_chunks=[lse]))
+        ops.fwd_step(q16, k16, v16, out, lse, None, None, None, 0, 0, causal, bias, seg, True, True, (sq, sk, sv), out32)
+        res = dict(q_chunks=[q16], out_chunks=[out32 if ops.scaled else out], lse_chunks=[lse], scales=(sq, sk, sv))
+        return (out32 if want_f32 else out), res
     lay = rs.choose_layout(world, Sq, k.shape[1], causal, layout)
+    if _transport() == "peer":
+        plan = rs.make_peer_plan(world, rank, Sq, k.shape[1], causal, lay)
+        return rp.run_forward(plan, q, k, v, bias, seg, causal, _peer_ops(precision),
+                              rp.CudaPeerTransport.get(group, q.device), want_f32)
+    ops = _ops_for(precision)
     plan = rs.make_plan(world, rank, Sq, k.shape[1], causal, lay, n_sub_first=rs.auto_sub(world, k.shape[1], lay))
-    if _transport() == "symm":
-        out, res = rxs.run_forward(plan, q, k, v, bias, seg, causal, group, ops, rxs.SymmMemBackend.get(group, q.device))
-    else:
-        out, res = rx.run_forward(plan, q, k, v, bias, seg, causal, group, ops)
+    out, res = rx.run_forward(plan, q, k, v, bias, seg, causal, group, ops)
     return out, _f32_residuals(ops, res)
 
 
 def ring_backward(res, k, v, dout, bias, seg, causal, group, rank, world, layout="auto", precision="bf16"):
     B, Sk, H, D = k.shape
     dev = k.device
-    ops = _ops_for(precision)
+    want_f32 = k.dtype == torch.float32
     if world == 1:
-        q, out, lse = res["q_chunks"][0], res["out_chunks"][0], res["lse_chunks"][0]
-        Sq = q.shape[1]
+        ops = _peer_ops(precision)
+        q16, out, lse = res["q_chunks"][0], res["out_chunks"][0], res["lse_chunks"][0]
+        sq, sk, sv = res["scales"]
+        Sq = q16.shape[1]
+        sdo = _local_scales(ops, (dout,))[0]
+        k16, v16, d16 = _stage_local(ops, k, sk), _stage_local(ops, v, sv), _stage_local(ops, dout, sdo)
         delta = torch.empty((B, H, Sq), dtype=torch.float32, device=dev)
-        bwd_prep(out, dout, delta)
-        lse = lse_for_bwd(lse)
+        ops.bwd_prep(out, d16, sdo, delta)
+        nlse = ops.lse_for_bwd(lse)
         dq_acc = torch.zeros((B, Sq, H, D), dtype=torch.float32, device=dev)
-        dk_acc = torch.zeros((B, Sk, H, D), dtype=torch.float32, device=dev)
-        dv_acc = torch.zeros((B, Sk, H, D), dtype=torch.float32, device=dev)
-        ops.bwd_step(q, k, v, dout, lse, delta, dq_acc, dk_acc, dv_acc, 0, 0, causal, bias, seg)
-        dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+        dk_acc = torch.empty((B, Sk, H, D), dtype=torch.float32, device=dev)     # written, not accumulated (init)
+        dv_acc = torch.empty((B, Sk, H, D), dtype=torch.float32, device=dev)
+        ops.bwd_step(q16, k16, v16, d16, nlse, delta, dq_acc, dk_acc, dv_acc, 0, 0, causal, bias, seg,
+                     (sq, sk, sv, sdo), True)
+        if want_f32:
+            return dq_acc, dk_acc, dv_acc
+        dq, dk, dv = [torch.empty(t.shape, dtype=torch.bfloat16, device=dev) for t in (dq_acc, dk_acc, dv_acc)]
         cast_f32_to_bf16(dq_acc, dq)
         cast_f32_to_bf16(dk_acc, dk)
         cast_f32_to_bf16(dv_acc, dv)
         return dq, dk, dv
     lay = rs.choose_layout(world, dout.shape[1], Sk, causal, layout)
+    if _transport() == "peer":
+        plan = rs.make_peer_plan(world, rank, dout.shape[1], Sk, causal, lay)
+        return rp.run_backward(plan, res, k, v, dout, bias, seg, causal, _peer_ops(precision),
+                               rp.CudaPeerTransport.get(group, dev), want_f32)
+    ops = _ops_for(precision)
     n_sub = rs.auto_sub(world, Sk, lay)
     plan = rs.make_plan(world, rank, dout.shape[1], Sk, causal, lay, n_sub_first=n_sub, n_sub_last=n_sub)
-    if _transport() == "symm":
-        return rxs.run_backward(plan, res, k, v, dout, bias, seg, causal, group, ops, rxs.SymmMemBackend.get(group, dev))
     return rx.run_backward(plan, res, k, v, dout, bias, seg, causal, group, ops)
 
 

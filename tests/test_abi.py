@@ -21,12 +21,12 @@ def test_library_exports_every_declared_symbol(lib):
     assert len(names) >= 13
     for n in names:
         assert hasattr(lib, n), "liblwm_b200.so does not export %s" % n
-    assert lib.lwm_abi_version() == 1
+    assert lib.lwm_abi_version() == 2
 
 
 def test_python_binding_covers_header():
     from lwm_b200 import _lib
-    bound = set(_lib._SIGNATURES) | {"lwm_last_error"}
+    bound = set(_lib._SIGNATURES) | {"lwm_last_error", "lwm_ring_ctx_heap", "lwm_ring_ctx_heap_bytes"}
     assert set(_declared()) <= bound
 
 

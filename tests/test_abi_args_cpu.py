@@ -26,8 +26,15 @@ BAD_CALLS = [
     ("lwm_attn_fwd_step", (P, P, P, N, N, N, N, N, 1, 2, 128, 128, 128, 0, 0, 1, N, 0, N, 0, 0.1, 1, 1, N), ARG, "last step"),
     ("lwm_attn_fwd_step", (P, P, P, P, P, N, N, N, 1, 2, 128, 128, 128, 0, 0, 1, N, 0, N, 0, 0.1, 1, 0, N), ARG, "carry"),
     ("lwm_attn_fwd_step", (P, P, P, P, P, N, N, N, 1, 2, 128, 128, 128, 1 << 31, 0, 1, N, 0, N, 0, 0.1, 1, 1, N), SHAPE, "int32"),
-    ("lwm_attn_bwd_step", (P, P, P, P, P, P, P, P, N, 1, 2, 128, 128, 128, 0, 0, 1, N, 0, N, 0, 0.1, N), ARG, "null"),
-    ("lwm_attn_bwd_step", (P, P, P, P, P, P, P, P, P, 1, 2, 128, 192, 128, 0, 0, 1, N, 0, N, 0, 0.1, N), SHAPE, "multiples of 128"),
+    ("lwm_attn_bwd_step", (P, P, P, P, P, P, P, P, N, 1, 2, 128, 128, 128, 0, 0, 1, N, 0, N, 0, 0.1, 0, N), ARG, "null"),
+    ("lwm_attn_bwd_step", (P, P, P, P, P, P, P, P, P, 1, 2, 128, 192, 128, 0, 0, 1, N, 0, N, 0, 0.1, 0, N), SHAPE, "multiples of 128"),
+    ("lwm_attn_absmax", (P, 2, 64, P, N), ARG, "bad arguments"),
+    ("lwm_attn_to_f16_scaled", (P, 1, P, P, 12, N), ARG, "n % 8"),
+    ("lwm_attn_bwd_prep_f16", (P, 0, P, P, P, 1, 2, 128, 64, N), SHAPE, "head_dim"),
+    ("lwm_reduce_cast_f32", (P, 17, P, 1, 64, N), ARG, "1..16 sources"),
+    ("lwm_ring_ctx_create", (3, 2, 1024, 0, P), ARG, "bad rank/world"),
+    ("lwm_ring_copy", (N, P, 16, N), ARG, "bad arguments"),
+    ("lwm_ring_signal", (N, 0, 0, 1, N), ARG, "null context"),
     ("lwm_attn_bwd_prep", (P, P, P, 1, 2, 128, 96, N), SHAPE, "head_dim"),
     ("lwm_attn_bwd_lse", (P, P, 0, N), ARG, "bad args"),
     ("lwm_attn_to_f16", (P, P, P, P, 12, N), SHAPE, "multiple of 8"),
@@ -62,7 +69,9 @@ def test_bad_arguments_are_rejected_with_a_message(lib, name, args, code, frag):
 
 GOOD_CALLS = [
     ("lwm_attn_fwd_step", (P, P, P, P, P, N, N, N, 1, 2, 128, 128, 128, 0, 0, 1, N, 0, N, 0, 0.1, 1, 1, N)),
-    ("lwm_attn_bwd_step", (P, P, P, P, P, P, P, P, P, 1, 2, 128, 128, 128, 0, 0, 1, N, 0, N, 0, 0.1, N)),
+    ("lwm_attn_bwd_step", (P, P, P, P, P, P, P, P, P, 1, 2, 128, 128, 128, 0, 0, 1, N, 0, N, 0, 0.1, 1, N)),
+    ("lwm_attn_absmax", (P, 1, 64, P, N)),
+    ("lwm_attn_bwd_prep_f16", (P, 0, P, P, P, 1, 2, 128, 128, N)),
     ("lwm_attn_rope", (P, P, 1, P, P, 1, P, P, 1, 8, 2, 2, 128, 0, N)),
     ("lwm_vq_conv2d", (P, P, P, P, P, N, P, 1, 16, 16, 64, 16, 16, 64, 64, 3, 1, 1, 3, 0, N)),
     ("lwm_vq_argmin", (P, P, P, N, P, 16, 8192, 64, N)),
