@@ -17,6 +17,11 @@ work is fixed as N grows.
           rank 0 inside the timed region, counted by lwm_b200._lib.launch_count()
   cpu_baseline / --impl reference   the CPU restatement of the reference algorithm (oracle/),
           timed on the host cores on a bounded sample of the same workload.
+  parity  before anything is timed, the SAME op on the SAME inputs (all N ranks) is checked against the float64
+          row-wise oracle (oracle/attn_rows.py): out / dq of one sampled query row per 128-row tile and dk / dv of
+          every key row, two heads, fp32 read-out; max relative Frobenius error over ranks (north_star bound 1e-3)
+  reference_probe   whether the reference's own JAX implementation (jax + the un-vendored `ringattention` package)
+          is importable on this box — if it ever is, the oracle is pinned against it on a small case right here
 """
 import argparse
 import json
@@ -162,6 +167,36 @@ def run_reference_arm(args, rank):
     print(json.dumps(line))
 
 
+def probe_reference():
+    """the ring-attention arithmetic lives in the un-vendored JAX package `ringattention`. If this box can
+    import it (it cannot in the stock image: no jax, no network), run its CPU path on a small case and pin
+    oracle/ring_blockwise.py against it; otherwise say why not."""
+    try:
+        import jax  # noqa: F401
+        import jax.numpy as jnp
+        from ringattention import ringattention_jax  # noqa: F401
+    except Exception as e:      # noqa: BLE001
+        return {"importable": False, "why": "%s: %s" % (type(e).__name__, str(e)[:120]),
+                "oracle_pinned_against_reference": False}
+    try:
+        import numpy as np
+        from oracle.attn_dense import attention_dense
+        rng = np.random.RandomState(0)
+        qn, kn, vn = [rng.randn(1, 512, 2, 64).astype(np.float32) for _ in range(3)]
+        bias = jnp.zeros((1, 1, 1, 512), jnp.float32)
+        out = ringattention_jax(jnp.asarray(qn), jnp.asarray(kn), jnp.asarray(vn), bias, None, axis_name=None,
+                                float32_logits=True, cache_idx=None,
+                                blockwise_kwargs=dict(causal_block_size=1, deterministic=True, dropout_rng=None,
+                                                      attn_pdrop=0.0, query_chunk_size=128, key_chunk_size=128,
+                                                      dtype=jnp.float32, policy=None, precision=None, prevent_cse=True))
+        ref = attention_dense(qn, kn, vn, causal=True)
+        err = float(np.linalg.norm(np.asarray(out, dtype=np.float64) - ref) / np.linalg.norm(ref))
+        return {"importable": True, "oracle_vs_reference_rel_err": err, "oracle_pinned_against_reference": bool(err < 1e-5)}
+    except Exception as e:      # noqa: BLE001
+        return {"importable": True, "why": "reference call failed: %s" % str(e)[:160],
+                "oracle_pinned_against_reference": False}
+
+
 def bench_vqgan(dev, peaks, world):
     """VQGAN encode of a 16-frame 256x256 clip (BASELINE 'VQGAN frames/s'), synthetic weights and pixels.
     Byte accounting = SURVEY.md §8d minimum-traffic model with fp32 activations: 815.5 MB / frame."""
@@ -207,10 +242,11 @@ def main():
     ap.add_argument("--layout", default="auto")
     ap.add_argument("--precision", default=None, choices=[None, "bf16", "fp16"],
                     help="attention precision mode (default: the package default, bf16)")
-    ap.add_argument("--e2e-overlap", action="store_true",
-                    help="(opt-in, not yet validated on hardware) e2e leg with step i+1's uploads and step i-1's "
-                         "downloads overlapping step i's kernels; default: copies serialised with the kernels")
+    ap.add_argument("--e2e-serial", action="store_true",
+                    help="e2e leg with the host<->device copies serialised with the kernels instead of double-buffered "
+                         "(default: step i+1's uploads and step i-1's downloads overlap step i's kernels)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="(debug) skip the oracle check that precedes the timing")
     ap.add_argument("--no-vqgan", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -238,11 +274,11 @@ def main():
     W, K = max(args.warmup, 3), args.steps
     peaks = load_peaks()
 
-    g = torch.Generator(device="cpu").manual_seed(1234 + rank)
-
-    def mk():
-        return torch.randn(1, Sl, H, D, generator=g, dtype=torch.float32).to(torch.bfloat16)
-    hq, hk, hv, hdo = [mk().pin_memory() for _ in range(4)]
+    from lwm_b200 import synthetic as syn
+    torch.set_num_threads(max(1, min(len(os.sched_getaffinity(0)), 64) // world))
+    # N(0,1) rounded to bf16; every (tensor, rank, head) has its own seeded stream so that any rank can rebuild any
+    # head of the whole sequence for the oracle check
+    hq, hk, hv, hdo = [syn.shard(n_, rank, Sl, H, D, 1234).pin_memory() for n_ in ("q", "k", "v", "do")]
     q, k, v, do = [t.to(dev) for t in (hq, hk, hv, hdo)]
     kwargs = dict(axis_name="sp", float32_logits=True, cache_idx=None,
                   blockwise_kwargs=dict(causal_block_size=1, deterministic=True, dropout_rng=None, attn_pdrop=0.0,
@@ -265,6 +301,26 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    # ---- parity of exactly this op / sharding / precision mode on exactly these inputs, before anything is timed
+    parity = None
+    if not args.no_parity:
+        from lwm_b200.selftest import sampled_parity
+        pe = sampled_parity(S, H, [0, H - 1], lambda a, b, c: ra.ringattention(a, b, c, None, None, **kwargs), dev, rank,
+                            world, 1234, shards=dict(q=q, k=k, v=v, do=do))
+        worst = max(pe[n_] for n_ in ("out", "dq", "dk", "dv"))
+        tp = torch.tensor([pe["out"], pe["dq"], pe["dk"], pe["dv"], pe["dq_unsampled_abs"], worst], device=dev)
+        tn = torch.tensor([float(pe["rows"]), float(pe["keys"])], device=dev)
+        if world > 1:
+            dist.all_reduce(tp, op=dist.ReduceOp.MAX)
+            dist.all_reduce(tn, op=dist.ReduceOp.SUM)
+        tp, tn = tp.tolist(), tn.tolist()
+        parity = {"max_rel": tp[5], "tol": 1e-3, "ok": bool(tp[5] < 1e-3 and tp[4] == 0.0),
+                  "per_tensor": {"out": tp[0], "dq": tp[1], "dk": tp[2], "dv": tp[3]},
+                  "rows": int(tn[0]), "key_rows": int(tn[1]), "heads_checked": [0, H - 1],
+                  "oracle": "oracle/attn_rows.py (float64, row-wise restatement of oracle/attn_dense.py); fp32 read-out "
+                            "of the op on the bench inputs, dO zero outside the sampled query rows; max over %d rank(s)"
+                            % world}
+        torch.set_num_threads(max(1, min(len(os.sched_getaffinity(0)), 64)))
     for _ in range(W):
         step()
     barrier()
@@ -296,12 +352,19 @@ def main():
         dq = torch.zeros(1, Sl, H, D, dtype=torch.float32, device=dev)
         dk = torch.zeros_like(dq)
         dv = torch.zeros_like(dq)
-        ra.fwd_step(q, k, v, out, lse, None, None, None, 0, 0, True, None, None, True, True)
+        prec = args.precision or ra._DEFAULT_PRECISION
+        if prec == "fp16":      # the tile kernels of the default mode: fp16 operand copies + their scales
+            (kq, sq_), (kk, sk_), (kv, sv_), (kdo, sd_) = [ra.to_f16(t) for t in (q, k, v, do)]
+            fsc, bsc = (sq_, sk_, sv_), (sq_, sk_, sv_, sd_)
+        else:
+            kq, kk, kv, kdo, fsc, bsc = q, k, v, do, None, None
+        ra.fwd_step(kq, kk, kv, out, lse, None, None, None, 0, 0, True, None, None, True, True, scales=fsc)
         ra.bwd_prep(out, do, delta)
-        nlse2 = ra.lse_for_bwd(lse)
-        for name, fn in (("fwd", lambda: ra.fwd_step(q, k, v, out, lse, None, None, None, 0, 0, True, None, None,
-                                                     True, True)),
-                         ("bwd", lambda: ra.bwd_step(q, k, v, do, nlse2, delta, dq, dk, dv, 0, 0, True, None, None))):
+        nlse2 = ra.lse_for_bwd(lse, f16=(prec == "fp16"))
+        for name, fn in (("fwd", lambda: ra.fwd_step(kq, kk, kv, out, lse, None, None, None, 0, 0, True, None, None,
+                                                     True, True, scales=fsc)),
+                         ("bwd", lambda: ra.bwd_step(kq, kk, kv, kdo, nlse2, delta, dq, dk, dv, 0, 0, True, None, None,
+                                                     scales=bsc))):
             fn()
             torch.cuda.synchronize()
             a, b2 = ev(), ev()
@@ -318,7 +381,8 @@ def main():
         tp = os.path.join(ROOT, "profiles", "ncu_attn_128k_r01.json")
         if S == S_TOTAL and os.path.exists(tp):
             traffic = json.load(open(tp))["attn_bwd_kernel"]["dram_total_bytes"]
-        roof = {"bound": "tensor", "kernel": "attn_bwd_kernel", "achieved": ach, "peak": peaks["sustained"],
+        roof = {"bound": "tensor", "kernel": "attn_bwd_kernel<%s>" % ("fp16 operands" if prec == "fp16" else "bf16 operands"),
+                "achieved": ach, "peak": peaks["sustained"],
                 "unit": "TFLOP/s", "frac": ach / peaks["sustained"], "traffic": traffic,
                 "traffic_note": "bytes per launch from profiles/ncu_attn_128k_r01.json; algorithmic minimum ~17 GB "
                                 "(q,k,v,dout once + dq/dk/dv fp32 read-modify-write); tensor-bound, HBM < 2 % busy",
@@ -382,8 +446,8 @@ def main():
     barrier()
     a, b2 = ev(), ev()
     a.record()
-    n_e2e = max(2, min(K, 3))
-    if args.e2e_overlap:
+    n_e2e = max(3, min(K, 6))
+    if not args.e2e_serial:
         e2e_pipelined(n_e2e)
     else:
         for _ in range(n_e2e):
@@ -416,11 +480,16 @@ def main():
             "frac_of_bf16_peak_per_gpu": total_flops / (ms * 1e-3) / 1e12 / world / peaks["sustained"],
             "e2e": {"value": S / (LAYERS * ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": bytes_in, "d2h_bytes_per_step": bytes_out,
-                    "copies": "overlapped with the previous/next step's kernels" if args.e2e_overlap
-                    else "serialised with the kernels"},
+                    "steps": n_e2e,
+                    "copies": "serialised with the kernels" if args.e2e_serial else
+                    "double-buffered: step i+1's uploads and step i-1's downloads overlap step i's kernels; all copies "
+                    "(first upload and last download included) inside the timed region"},
             "gpu_launches": gpu_launches,
             "clocks": clocks,
+            "reference_probe": probe_reference(),
         }
+        if parity:
+            line["parity"] = parity
         if roof:
             line["roofline"] = roof
         if vq:

@@ -67,8 +67,11 @@ int lwm_attn_fwd_step(const void* q, const void* k, const void* v, void* out, fl
 
 /* Ring attention, backward.
  * lwm_attn_bwd_prep: delta[b,h,s] = sum_d dout[b,s,h,d] * out[b,s,h,d]  (fp32), once per backward.
- * lwm_attn_bwd_lse:  nlse2[i] = -lse[i]*log2(e) (-inf for rows whose lse is at the masked level), once per backward;
- *                    lwm_attn_bwd_step takes THIS array as its `lse` argument (the per-tile kernel is exp-bound).
+ * lwm_attn_bwd_lse:  nlse2[i] = -lse[i]*log2(e) + offset_log2 (-inf for rows whose lse is at the masked level), once per
+ *                    backward; lwm_attn_bwd_step takes THIS array as its `lse` argument (the per-tile kernel is
+ *                    exp-bound). offset_log2 = 0 for lwm_attn_bwd_step (bf16 operands) and
+ *                    LWM_ATTN_F16_P_BOOST_LOG2 for lwm_attn_bwd_step_f16: the fp16 kernel keeps P^T * 2^14 so that the
+ *                    normalised probabilities of a 128K .. 1M-key row stay normal fp16 numbers.
  * lwm_attn_bwd_step: one ring step of the reference's custom_vjp bwd (SURVEY.md Appendix A `bwd`):
  *   recomputes P from (q, k, lse), accumulates
  *     dq_acc [B,Sq,H,D] fp32 += dS K / sqrt(D)        (atomic fp32 tile reductions; zero it first)
@@ -78,8 +81,9 @@ int lwm_attn_fwd_step(const void* q, const void* k, const void* v, void* out, fl
  *   dkv_init != 0: the dk_acc/dv_acc rows of the key tiles this launch visits are WRITTEN instead of accumulated
  *   (first visit of a block: saves zero-filling the accumulators); key tiles no query row can see are zero-filled.
  */
+#define LWM_ATTN_F16_P_BOOST_LOG2 14.0f
 int lwm_attn_bwd_prep(const void* out, const void* dout, float* delta, int B, int H, int Sq, int D, void* stream);
-int lwm_attn_bwd_lse(const float* lse, float* nlse2, long long n, void* stream);
+int lwm_attn_bwd_lse(const float* lse, float* nlse2, long long n, float offset_log2, void* stream);
 int lwm_attn_bwd_step(const void* q, const void* k, const void* v, const void* dout, const float* lse,
                       const float* delta, float* dq_acc, float* dk_acc, float* dv_acc, int B, int H, int Sq,
                       int Sk, int D, long long q_pos0, long long k_pos0, int causal, const float* bias,
@@ -216,6 +220,22 @@ int lwm_vq_conv2d(const void* a_hi, const void* a_lo, const void* w_hi, const vo
                   int Cout_pad, int ksize, int stride, int pad, int n_pass, int clip, void* stream);
 int lwm_vq_conv_cin3(const float* x, const float* w_hwio, const float* bias, float* y, int N, int H, int W, int Cout,
                      void* stream);
+/* "fp16x2" precision mode of the conv stack (the default: <= 1e-3 vs the fp32 reference at 2x instead of 3x the
+ * algorithmic tensor work and half the operand bytes):
+ * lwm_vq_prep_f16    like lwm_vq_prep, but ONE fp16 operand plane [N,H',W',C_pad].
+ * lwm_vq_conv2d_f16  activation = that plane; weights split w = hi + lo (two fp16, pre-multiplied by the power of two
+ *                    1/w_scale_inv so that lo stays a normal fp16) and STACKED along Cout: w_stacked
+ *                    [taps][Cout_pad/BN][2*BN][C_pad], BN = largest multiple of 16 <= 128 dividing Cout_pad, rows [0,BN) = hi, [BN,2BN) = lo. One
+ *                    128 x 2BN UMMA yields A.hi | A.lo side by side; the epilogue adds them, applies w_scale_inv, bias,
+ *                    residual, clip. gn_stats_out (optional; zeroed by the caller; [N, groups, 2] float64): the epilogue
+ *                    also accumulates (sum, sum of squares) of the OUTPUT per (sample, group) — the statistics of the
+ *                    GroupNorm that consumes this tensor (vqgan.py:251,254,161,181), so lwm_vq_gn_stats' extra pass
+ *                    over the activation disappears. */
+int lwm_vq_prep_f16(const float* x, const double* gn_stats, const float* gamma, const float* beta, void* out, int N, int H,
+                    int W, int C, int C_pad, int groups, int upsample2x, float eps, void* stream);
+int lwm_vq_conv2d_f16(const void* a, const void* w_stacked, const float* bias, const float* residual, float* out,
+                      double* gn_stats_out, int N, int Hin, int Win, int Cpad, int Ho, int Wo, int Cout, int Cout_pad,
+                      int ksize, int stride, int pad, float w_scale_inv, int groups, int clip, void* stream);
 int lwm_vq_argmin(const float* z, const float* codebook, int* idx, float* zq_st, void* workspace, int N, int n_e,
                   int e_dim, void* stream);
 int lwm_vq_gather(const int* idx, const float* codebook, float* out, long long N, int n_e, int e_dim, void* stream);

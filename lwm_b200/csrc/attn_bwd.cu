@@ -72,6 +72,12 @@ LWM_DEVICE void load_tile_nb(uint8_t* dst, const CUtensorMap* tm, uint64_t* bar,
 // boosted by 2^8 before rounding (keeps it clear of fp16 subnormals); every scale factor is undone in
 // fp32 where the results leave the tensor pipe (dQ drain, dK/dV epilogue).
 constexpr float kDsBoost = 256.0f;
+// P^T = exp(s - lse) is a NORMALISED probability: at 128K .. 1M keys a typical entry is 1e-5 .. 1e-6, below fp16's
+// smallest normal (6.1e-5), where it would lose its 11 bits (measured: dV error 1.2e-3 at S=131072 against 2e-4 at 2K).
+// The fp16 kernel therefore works on P * 2^14 (<= 16384, never overflows; normal down to 3.7e-9): the host folds the
+// +14 into the pre-scaled lse (lwm_attn_bwd_lse, offset_log2 = LWM_ATTN_F16_P_BOOST_LOG2) and the factor is undone in
+// fp32 in the dV epilogue and in the dS scale.
+constexpr float kPBoostInv = 1.0f / 16384.0f;
 template <bool kF16>
 __global__ void __launch_bounds__(kBwdThreads, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
@@ -332,7 +338,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     // fp16 mode: logits scale picks up scale_q*scale_k; dP = dO V^T picks up scale_do*scale_v
     const float scale_log2 = p.scale_log2 * (kF16 ? (*p.scale_q) * (*p.scale_k) : 1.0f);
     const float dp_mul = kF16 ? (*p.scale_do) * (*p.scale_v) : 1.0f;
-    const float ds_mul = p.scale * (kF16 ? kDsBoost : 1.0f);
+    const float ds_mul = p.scale * (kF16 ? kDsBoost * kPBoostInv : 1.0f);   // pr holds P * 2^14 in fp16 mode
     float pr[64];
     // prof slots 8..10: q_full, s_full, dp_full ; 11: total (thread 0 only)
     WaitProf wp;
@@ -466,7 +472,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     tc_fence_after();
     {
       // dK = (dS*boost)^T Q16 * scale_q / boost ; dV = P^T dO16 * scale_do
-      const float acc_mul = kF16 ? (wg == 0 ? (*p.scale_q) * (1.0f / kDsBoost) : (*p.scale_do)) : 1.0f;
+      const float acc_mul = kF16 ? (wg == 0 ? (*p.scale_q) * (1.0f / kDsBoost) : (*p.scale_do) * kPBoostInv) : 1.0f;
       const uint32_t tAcc = tmem + lane_off + (wg == 0 ? RDK : RDV);
       float* acc = (wg == 0 ? p.dk_acc : p.dv_acc) +
                    ((((long long)b * p.Sk + (long long)n * kTile + r) * p.H + h) * kHeadDim);

@@ -59,10 +59,10 @@ __global__ void bwd_prep_f32_kernel(const float* __restrict__ out, const __nv_bf
 // nlse2 = -lse * log2(e), with rows whose lse sits at the masked level (never saw an unmasked key: padded rows)
 // mapped to -inf so that the backward gives them p = 0 — hoisted out of the tile kernel, where every key-tile CTA
 // would redo it for every query column.
-__global__ void lse_to_nlse2_kernel(const float* __restrict__ lse, float* __restrict__ nlse2, long long n) {
+__global__ void lse_to_nlse2_kernel(const float* __restrict__ lse, float* __restrict__ nlse2, long long n, float offset) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const float l = lse[i];
-    nlse2[i] = (l < -1.0e29f) ? -INFINITY : -l * kLog2e;
+    nlse2[i] = (l < -1.0e29f) ? -INFINITY : fmaf(-l, kLog2e, offset);
   }
 }
 
@@ -250,12 +250,12 @@ extern "C" int lwm_attn_bwd_prep_f32(const float* out_f32, const void* dout, flo
   return lwm_check_launch("bwd_prep_f32_kernel");
 }
 
-extern "C" int lwm_attn_bwd_lse(const float* lse, float* nlse2, long long n, void* stream) {
+extern "C" int lwm_attn_bwd_lse(const float* lse, float* nlse2, long long n, float offset_log2, void* stream) {
   if (!lse || !nlse2 || n <= 0) return lwm_fail(LWM_ERR_ARG, "attn_bwd_lse: bad args");
   if (!lwm_check_device()) return LWM_ERR_DEVICE;
   const long long want = (n + 255) / 256;
   lse_to_nlse2_kernel<<<unsigned(want < 148LL * 8 ? want : 148LL * 8), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      lse, nlse2, n);
+      lse, nlse2, n, offset_log2);
   return lwm_check_launch("lse_to_nlse2_kernel");
 }
 

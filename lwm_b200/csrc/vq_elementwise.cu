@@ -51,6 +51,8 @@ __global__ void gn_stats_kernel(const float* __restrict__ x, double* __restrict_
 // prep: y = [silu(gn(x))] at (h>>up, w>>up); hi = bf16(y); lo = bf16(y - hi). Output planes have
 // C_pad >= C channels (multiple of 64 for the conv's 128-byte TMA rows); padding channels are zero.
 // ------------------------------------------------------------------------------------------------
+// kF16: ONE fp16 plane (the fp16x2 conv mode: 11 significant bits, half the bytes of the hi+lo pair) instead.
+template <bool kF16>
 __global__ void prep_kernel(const float* __restrict__ x, const double* __restrict__ stats,
                             const float* __restrict__ gamma, const float* __restrict__ beta,
                             __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int N, int H, int W,
@@ -97,15 +99,21 @@ __global__ void prep_kernel(const float* __restrict__ x, const double* __restric
       }
     }
     uint32_t h4[4], l4[4];
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const __nv_bfloat16 h0 = __float2bfloat16_rn(y[2 * e]), h1 = __float2bfloat16_rn(y[2 * e + 1]);
-      h4[e] = uint32_t(__bfloat16_as_ushort(h0)) | (uint32_t(__bfloat16_as_ushort(h1)) << 16);
-      l4[e] = pack_bf16x2(y[2 * e] - __bfloat162float(h0), y[2 * e + 1] - __bfloat162float(h1));
-    }
     const size_t o = (((size_t)n * Ho + ho) * Wo + wo) * C_pad + c0;
-    *reinterpret_cast<uint4*>(hi + o) = make_uint4(h4[0], h4[1], h4[2], h4[3]);
-    if (write_lo) *reinterpret_cast<uint4*>(lo + o) = make_uint4(l4[0], l4[1], l4[2], l4[3]);
+    if constexpr (kF16) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) h4[e] = pack_f16x2(y[2 * e], y[2 * e + 1]);
+      *reinterpret_cast<uint4*>(hi + o) = make_uint4(h4[0], h4[1], h4[2], h4[3]);
+    } else {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const __nv_bfloat16 h0 = __float2bfloat16_rn(y[2 * e]), h1 = __float2bfloat16_rn(y[2 * e + 1]);
+        h4[e] = uint32_t(__bfloat16_as_ushort(h0)) | (uint32_t(__bfloat16_as_ushort(h1)) << 16);
+        l4[e] = pack_bf16x2(y[2 * e] - __bfloat162float(h0), y[2 * e + 1] - __bfloat162float(h1));
+      }
+      *reinterpret_cast<uint4*>(hi + o) = make_uint4(h4[0], h4[1], h4[2], h4[3]);
+      if (write_lo) *reinterpret_cast<uint4*>(lo + o) = make_uint4(l4[0], l4[1], l4[2], l4[3]);
+    }
   }
 }
 
@@ -316,10 +324,29 @@ extern "C" int lwm_vq_prep(const float* x, const double* gn_stats, const float* 
   const int threads = 256;
   const size_t want = (total + threads - 1) / threads;
   const unsigned blocks = unsigned(want < 148u * 32 ? want : 148u * 32);
-  prep_kernel<<<blocks, threads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  prep_kernel<false><<<blocks, threads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       x, gn_stats, gamma, beta, reinterpret_cast<__nv_bfloat16*>(hi), reinterpret_cast<__nv_bfloat16*>(lo), N, H, W,
       C, C_pad, groups, upsample2x ? 1 : 0, eps, lo != nullptr);
   return lwm_check_launch("prep_kernel");
+}
+
+// fp16x2 conv mode: y = [silu(groupnorm(x))] (optionally nearest-2x upsampled) as ONE fp16 plane [N,H',W',C_pad].
+extern "C" int lwm_vq_prep_f16(const float* x, const double* gn_stats, const float* gamma, const float* beta, void* out,
+                               int N, int H, int W, int C, int C_pad, int groups, int upsample2x, float eps,
+                               void* stream) {
+  if (!x || !out) return lwm_fail(LWM_ERR_ARG, "vq_prep_f16: null pointer");
+  if (C % 4 || C_pad % 8 || C_pad < C) return lwm_fail(LWM_ERR_SHAPE, "vq_prep_f16: C % 4 and C_pad % 8 required");
+  if (gn_stats && (!gamma || !beta || C % groups || (C / groups) % 4))
+    return lwm_fail(LWM_ERR_SHAPE, "vq_prep_f16: GroupNorm needs gamma/beta and C/groups % 4 == 0");
+  if (!lwm_check_device()) return LWM_ERR_DEVICE;
+  const size_t total = (size_t)N * (H << upsample2x) * (W << upsample2x) * (C_pad / 8);
+  const int threads = 256;
+  const size_t want = (total + threads - 1) / threads;
+  const unsigned blocks = unsigned(want < 148u * 32 ? want : 148u * 32);
+  prep_kernel<true><<<blocks, threads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      x, gn_stats, gamma, beta, reinterpret_cast<__nv_bfloat16*>(out), nullptr, N, H, W, C, C_pad, groups,
+      upsample2x ? 1 : 0, eps, 0);
+  return lwm_check_launch("prep_kernel<f16>");
 }
 
 extern "C" int lwm_vq_conv_cin3(const float* x, const float* w_hwio, const float* bias, float* y, int N, int H, int W,

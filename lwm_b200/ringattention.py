@@ -226,10 +226,15 @@ def bwd_prep(out, dout, delta, stream=None):
               _lib.stream_ptr(stream))
 
 
-def lse_for_bwd(lse, stream=None):
-    """-lse*log2(e) (masked-level rows -> -inf), computed once per backward: what bwd_step takes as `lse`."""
+F16_P_BOOST_LOG2 = 14.0      # include/lwm_b200.h: LWM_ATTN_F16_P_BOOST_LOG2
+
+
+def lse_for_bwd(lse, stream=None, f16=False):
+    """-lse*log2(e) (masked-level rows -> -inf), computed once per backward: what bwd_step takes as `lse`.
+    f16=True: for the fp16-operand kernel, which keeps P^T * 2^14 (the +14 rides on this array)."""
     out = torch.empty_like(lse)
-    _lib.call("lwm_attn_bwd_lse", _lib.ptr(lse), _lib.ptr(out), lse.numel(), _lib.stream_ptr(stream))
+    _lib.call("lwm_attn_bwd_lse", _lib.ptr(lse), _lib.ptr(out), lse.numel(), F16_P_BOOST_LOG2 if f16 else 0.0,
+              _lib.stream_ptr(stream))
     return out
 
 
@@ -300,6 +305,10 @@ class CudaOpsF16(CudaOps):
         fwd_step(q16, k16, v16, out, lse, acc_o, acc_m, acc_l, q_pos0, k_pos0, causal, bias, seg, first, last,
                  scales=(sq, sk, sv), out_f32=o32)
 
+    @staticmethod
+    def lse_for_bwd(lse):
+        return lse_for_bwd(lse, f16=True)
+
     def bwd_step(self, q, k, v, dout, lse, delta, dq_acc, dk_acc, dv_acc, q_pos0, k_pos0, causal, bias, seg):
         (q16, sq), (k16, sk), (v16, sv), (d16, sd) = self._f16(q), self._f16(k), self._f16(v), self._f16(dout)
         bwd_step(q16, k16, v16, d16, lse, delta, dq_acc, dk_acc, dv_acc, q_pos0, k_pos0, causal, bias, seg,
@@ -355,7 +364,9 @@ class PeerOpsF16:
         _lib.call("lwm_attn_bwd_prep_f16", _lib.ptr(out), _dt(out), _lib.ptr(dout16), _lib.ptr(sdo), _lib.ptr(delta),
                   B, H, Sq, D, _lib.stream_ptr())
 
-    lse_for_bwd = staticmethod(lse_for_bwd)
+    @staticmethod
+    def lse_for_bwd(lse):
+        return lse_for_bwd(lse, f16=True)
 
     @staticmethod
     def bwd_step(q, k, v, dout, lse, delta, dq_acc, dk_acc, dv_acc, q_pos0, k_pos0, causal, bias, seg, scales, init):
@@ -388,6 +399,10 @@ class PeerOpsBf16(PeerOpsF16):
     @staticmethod
     def bwd_prep(out, dout, sdo, delta):
         bwd_prep(out, dout, delta)
+
+    @staticmethod
+    def lse_for_bwd(lse):
+        return lse_for_bwd(lse, f16=False)
 
     @staticmethod
     def bwd_step(q, k, v, dout, lse, delta, dq_acc, dk_acc, dv_acc, q_pos0, k_pos0, causal, bias, seg, scales, init):

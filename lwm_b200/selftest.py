@@ -10,14 +10,16 @@ def _rel(x, ref):
     return float(np.linalg.norm(x - ref) / max(np.linalg.norm(ref), 1e-30))
 
 
-def sampled_parity(S_total, H, check_heads, op, device, rank=0, world=1, base_seed=1234, sync=None):
+def sampled_parity(S_total, H, check_heads, op, device, rank=0, world=1, base_seed=1234, shards=None):
     """Parity of the attention op at BASELINE sizes (32K .. 128K tokens), where the dense oracle does not fit: this
     rank's shards of the seeded synthetic q/k/v (lwm_b200/synthetic.py) go through `op` (forward + backward) with a dO
     that is zero outside one sampled query row per 128-row tile (+ the last 128 rows of the sequence); the float64
     row-wise oracle (oracle/attn_rows.py) then gives, for each head in `check_heads`, the exact out / dq of the sampled
     rows and dk / dv of EVERY key row. Inputs are float32 tensors holding bf16-representable values, so `op` returns
     its un-rounded fp32 results. Returns {name: relative Frobenius error over this rank's rows}.
-    op(q, k, v) -> out must be differentiable (the public ringattention op bound to the caller's process group)."""
+    op(q, k, v) -> out must be differentiable (the public ringattention op bound to the caller's process group).
+    shards: optional dict(q, k, v, do) of this rank's DEVICE tensors [1, S_total/world, H, 128] already built with
+    synthetic.shard(name, rank, ...) and the same base_seed (bench.py passes its timed inputs)."""
     from oracle.attn_rows import attention_rows, sample_rows
     from . import synthetic as syn
     D = 128
@@ -25,15 +27,15 @@ def sampled_parity(S_total, H, check_heads, op, device, rank=0, world=1, base_se
     rows = sample_rows(S_total, seed=base_seed)
     lo, hi = rank * Sl, (rank + 1) * Sl
     mine = rows[(rows >= lo) & (rows < hi)]
-    q, k, v, do = [syn.shard(n_, rank, Sl, H, D, base_seed, torch.float32) for n_ in ("q", "k", "v", "do")]
+    if shards is None:
+        shards = {n_: syn.shard(n_, rank, Sl, H, D, base_seed, torch.bfloat16).to(device) for n_ in ("q", "k", "v", "do")}
     keep = torch.zeros(Sl, dtype=torch.bool)
     keep[mine - lo] = True
-    do[0, ~keep] = 0
-    qd, kd, vd = [t.to(device).requires_grad_(True) for t in (q, k, v)]
+    do = shards["do"].float()
+    do[0, (~keep).to(device)] = 0
+    qd, kd, vd = [shards[n_].float().requires_grad_(True) for n_ in ("q", "k", "v")]
     out = op(qd, kd, vd)
-    out.backward(do.to(device))
-    if sync is not None:
-        sync()
+    out.backward(do)
     torch.cuda.synchronize()
     got = dict(out=out.detach()[0].double().cpu(), dq=qd.grad[0].double().cpu(), dk=kd.grad[0].double().cpu(),
                dv=vd.grad[0].double().cpu())

@@ -10,9 +10,12 @@ NHWC fp32 activations and the flax parameter tree ({'encoder': {'Conv_0': {'kern
 weights are re-packed once into the conv kernel's layout ([tap][Cout_pad][Cin_pad] bf16 hi/lo).
 
 All arithmetic happens in liblwm_b200.so (include/lwm_b200.h: lwm_vq_*). torch only owns memory.
-precision: 'bf16x3' (default) feeds the tensor cores split-bf16 operands (x = hi + lo, three MMAs)
-for fp32-class accuracy — the reference computes these convs in fp32; 'bf16' is the single-pass
-fast mode (≈1e-2 end-to-end relative error, 99.6 % code agreement on synthetic weights).
+precision (the reference computes these convs in fp32):
+  'fp16x2' (default)  activation = one fp16 plane, weights split hi + lo (two fp16) stacked along Cout so that one wide
+                      UMMA does both halves; GroupNorm statistics come out of the producing conv's epilogue. 8.9e-4
+                      end-to-end relative error on the encoder latents (<= 1e-3), 2x the algorithmic tensor work.
+  'bf16x3'            both operands split into two bf16, three MMAs: fp32-class accuracy (1e-5), 3x the tensor work.
+  'bf16'              single pass (≈1e-2 end-to-end relative error, 99.6 % code agreement on synthetic weights).
 """
 import pickle
 
@@ -22,6 +25,11 @@ import torch
 from . import _lib
 
 GN_GROUPS, GN_EPS = 32, 1e-6   # flax nn.GroupNorm() defaults
+# 'fp16x2' is a MIXED mode: convs with at least this many output pixels per frame (the 64x64 .. 256x256 levels: 85 % of
+# the encoder's FLOPs and bytes) run the 2-MMA fp16 scheme, the small deep layers keep the 3-MMA split-bf16 scheme.
+# Measured with the oracle's operand-rounding emulation: 6.7e-4 (encode) / 5.9e-4 (decode) end-to-end
+# relative error, against 8.9e-4 / 8.8e-4 with every layer on the 2-MMA scheme — margin under the 1e-3 bound.
+MIXED_MIN_PIXELS = 64 * 64
 
 
 class VQGANConfig:
@@ -133,15 +141,27 @@ class PackedConv:
         self.w_hi = full.to(torch.bfloat16).contiguous()
         self.w_lo = (full - self.w_hi.float()).to(torch.bfloat16).contiguous()
         self.w_hwio = w                                  # kept for the Cin=3 CUDA-core path
+        # fp16x2 mode: w * 2^k = hi + lo (two fp16; k puts |w|max in [2^12, 2^13) so that lo stays a normal fp16),
+        # stacked per N tile of BN output channels: [taps][Cout_pad/BN][hi rows | lo rows][Cpad]
+        wmax = float(full.abs().max())
+        k = 12 - int(np.floor(np.log2(wmax))) if wmax > 0 else 0
+        self.w_scale_inv = float(2.0 ** -k)
+        sc = full * float(2.0 ** k)
+        hi16 = sc.to(torch.float16)
+        lo16 = (sc - hi16.float()).to(torch.float16)
+        self.bn = max(d for d in range(16, 129, 16) if self.cout_pad % d == 0)   # same rule as lwm_vq_conv2d_f16
+        taps, nt = self.k * self.k, self.cout_pad // self.bn
+        self.w_stack = torch.cat([hi16.view(taps, nt, self.bn, self.cpad), lo16.view(taps, nt, self.bn, self.cpad)],
+                                 dim=2).contiguous()
 
 
 class Ops:
     """Thin typed wrappers over the C ABI (every method allocates its outputs with torch)."""
 
-    def __init__(self, precision="bf16x3"):
-        if precision not in ("bf16x3", "bf16"):
-            raise ValueError("precision must be 'bf16x3' or 'bf16'")
-        self.n_pass = 3 if precision == "bf16x3" else 1
+    def __init__(self, precision="fp16x2"):
+        if precision not in ("fp16x2", "bf16x3", "bf16"):
+            raise ValueError("precision must be 'fp16x2', 'bf16x3' or 'bf16'")
+        self.n_pass = {"fp16x2": 2, "bf16x3": 3, "bf16": 1}[precision]
 
     def gn_stats(self, x):
         N, H, W, C = x.shape
@@ -149,30 +169,67 @@ class Ops:
         _lib.call("lwm_vq_gn_stats", _lib.ptr(x), _lib.ptr(st), N, H, W, C, GN_GROUPS, _lib.stream_ptr())
         return st
 
-    def prep(self, x, gn=None, upsample=False, cpad=None):
-        """-> (hi, lo) operand planes [N,H',W',Cpad] bf16; gn = flax GroupNorm params or None."""
+    def passes_for(self, out_pixels):
+        """MMA scheme of one conv: 1 bf16, 2 fp16 activation x stacked fp16 hi|lo weights, 3 split-bf16"""
+        if self.n_pass != 2:
+            return self.n_pass
+        return 2 if out_pixels >= MIXED_MIN_PIXELS else 3
+
+    def conv_gn(self, x, pc, gn=None, upsample=False, stride=1, residual=None, clip=False, want_stats=False):
+        """[GroupNorm + SiLU ->] [nearest 2x ->] conv: operand preparation and conv with the scheme the mode assigns to
+        this layer."""
+        s = 2 if upsample else 1
+        n_pass = self.passes_for((x.shape[1] * s // stride) * (x.shape[2] * s // stride))
+        return self.conv(self.prep(x, gn, upsample, n_pass=n_pass), pc, stride=stride, residual=residual, clip=clip,
+                         want_stats=want_stats)
+
+    def prep(self, x, gn=None, upsample=False, cpad=None, n_pass=None):
+        """-> (hi, lo) operand planes [N,H',W',Cpad]: bf16 hi (+ bf16 lo), or one fp16 plane (n_pass 2);
+        gn = flax GroupNorm params or None."""
+        n_pass = n_pass or self.n_pass
         N, H, W, C = x.shape
         cpad = cpad or _pad_to(C, 64)
         s = 2 if upsample else 1
-        hi = torch.empty(N, H * s, W * s, cpad, dtype=torch.bfloat16, device=x.device)
-        lo = torch.empty_like(hi) if self.n_pass == 3 else None
         st = g = b = None
         if gn is not None:
-            st, g, b = self.gn_stats(x), gn["scale"], gn["bias"]
+            # the producing conv's epilogue may already have accumulated this tensor's statistics (fp16x2 mode)
+            st = getattr(x, "_gn_stats", None)
+            if st is None:
+                st = self.gn_stats(x)
+            g, b = gn["scale"], gn["bias"]
+        if n_pass == 2:
+            hi = torch.empty(N, H * s, W * s, cpad, dtype=torch.float16, device=x.device)
+            _lib.call("lwm_vq_prep_f16", _lib.ptr(x), _lib.ptr(st), _lib.ptr(g), _lib.ptr(b), _lib.ptr(hi), N, H, W, C,
+                      cpad, GN_GROUPS, int(upsample), GN_EPS, _lib.stream_ptr())
+            return hi, None
+        hi = torch.empty(N, H * s, W * s, cpad, dtype=torch.bfloat16, device=x.device)
+        lo = torch.empty_like(hi) if n_pass == 3 else None
         _lib.call("lwm_vq_prep", _lib.ptr(x), _lib.ptr(st), _lib.ptr(g), _lib.ptr(b), _lib.ptr(hi), _lib.ptr(lo),
                   N, H, W, C, cpad, GN_GROUPS, int(upsample), GN_EPS, _lib.stream_ptr())
         return hi, lo
 
-    def conv(self, planes, pc, stride=1, residual=None, clip=False):
+    def conv(self, planes, pc, stride=1, residual=None, clip=False, want_stats=False):
+        """want_stats: the output feeds a GroupNorm — have the epilogue accumulate its statistics (fp16x2 mode)."""
         hi, lo = planes
         N, Hin, Win, cpad = hi.shape
         assert cpad == pc.cpad, (cpad, pc.cpad)
         Ho, Wo = Hin // stride, Win // stride
         pad = (pc.k // 2) if stride == 1 else 0
         out = torch.empty(N, Ho, Wo, pc.cout, dtype=torch.float32, device=hi.device)
+        n_pass = 2 if hi.dtype == torch.float16 else (3 if lo is not None else 1)
+        if n_pass == 2:
+            st = None
+            if want_stats and pc.cout % 16 == 0 and pc.cout % GN_GROUPS == 0 and (pc.cout // GN_GROUPS) % 4 == 0:
+                st = torch.zeros(N, GN_GROUPS, 2, dtype=torch.float64, device=hi.device)
+            _lib.call("lwm_vq_conv2d_f16", _lib.ptr(hi), _lib.ptr(pc.w_stack), _lib.ptr(pc.bias), _lib.ptr(residual),
+                      _lib.ptr(out), _lib.ptr(st), N, Hin, Win, cpad, Ho, Wo, pc.cout, pc.cout_pad, pc.k, stride, pad,
+                      pc.w_scale_inv, GN_GROUPS, int(clip), _lib.stream_ptr())
+            if st is not None:
+                out._gn_stats = st
+            return out
         _lib.call("lwm_vq_conv2d", _lib.ptr(hi), _lib.ptr(lo), _lib.ptr(pc.w_hi),
-                  _lib.ptr(pc.w_lo if self.n_pass == 3 else None), _lib.ptr(pc.bias), _lib.ptr(residual),
-                  _lib.ptr(out), N, Hin, Win, cpad, Ho, Wo, pc.cout, pc.cout_pad, pc.k, stride, pad, self.n_pass,
+                  _lib.ptr(pc.w_lo if n_pass == 3 else None), _lib.ptr(pc.bias), _lib.ptr(residual),
+                  _lib.ptr(out), N, Hin, Win, cpad, Ho, Wo, pc.cout, pc.cout_pad, pc.k, stride, pad, n_pass,
                   int(clip), _lib.stream_ptr())
         return out
 
@@ -214,19 +271,19 @@ def _pack_tree(p, dev):
 # ---- the reference's modules, as functions over packed parameter sub-trees -------------------------
 def ResnetBlock(ops, x, p):
     """lwm/vqgan.py:242-263: GN -> SiLU -> Conv3x3 -> GN -> SiLU -> Conv3x3 (+ 1x1 shortcut) + residual."""
-    h = ops.conv(ops.prep(x, p["GroupNorm_0"]), p["Conv_0"])
-    res = ops.conv(ops.prep(x), p["Conv_2"]) if "Conv_2" in p else x
-    return ops.conv(ops.prep(h, p["GroupNorm_1"]), p["Conv_1"], residual=res)
+    h = ops.conv_gn(x, p["Conv_0"], gn=p["GroupNorm_0"], want_stats=True)
+    res = ops.conv_gn(x, p["Conv_2"]) if "Conv_2" in p else x
+    return ops.conv_gn(h, p["Conv_1"], gn=p["GroupNorm_1"], residual=res, want_stats=True)
 
 
 def Downsample(ops, x, p):
     """lwm/vqgan.py:286-303: zero-pad bottom/right, 3x3 stride-2 VALID conv."""
-    return ops.conv(ops.prep(x), p["Conv_0"], stride=2)
+    return ops.conv_gn(x, p["Conv_0"], stride=2, want_stats=True)
 
 
 def Upsample(ops, x, p):
     """lwm/vqgan.py:306-319: nearest 2x then 3x3 SAME conv (the resize is fused into the operand prep)."""
-    return ops.conv(ops.prep(x, upsample=True), p["Conv_0"])
+    return ops.conv_gn(x, p["Conv_0"], upsample=True, want_stats=True)
 
 
 def VectorQuantizer(ops, z, p, encoding_indices=None):
@@ -243,7 +300,7 @@ def VectorQuantizer(ops, z, p, encoding_indices=None):
 class VQGANModel:
     """lwm/vqgan.py:105-146 on packed parameters."""
 
-    def __init__(self, config, params, device="cuda", precision="bf16x3"):
+    def __init__(self, config, params, device="cuda", precision="fp16x2"):
         self.config = config
         self.device = torch.device(device)
         self.ops = Ops(precision)
@@ -252,7 +309,7 @@ class VQGANModel:
     def encoder(self, x):
         cfg, p, ops = self.config, self.p["encoder"], self.ops
         assert x.shape[1] == x.shape[2] == cfg.resolution, tuple(x.shape)   # vqgan.py:154
-        h = ops.conv_cin3(x, p["Conv_0"]) if x.shape[-1] == 3 else ops.conv(ops.prep(x), p["Conv_0"])
+        h = ops.conv_cin3(x, p["Conv_0"]) if x.shape[-1] == 3 else ops.conv_gn(x, p["Conv_0"], want_stats=True)
         for i in range(cfg.num_resolutions):
             blk = p["DownsamplingBlock_%d" % i]
             for j in range(cfg.num_res_blocks):
@@ -261,11 +318,11 @@ class VQGANModel:
                 h = Downsample(ops, h, blk["Downsample_0"])
         h = ResnetBlock(ops, h, p["MidBlock_0"]["ResnetBlock_0"])
         h = ResnetBlock(ops, h, p["MidBlock_0"]["ResnetBlock_1"])
-        return ops.conv(ops.prep(h, p["GroupNorm_0"]), p["Conv_1"])
+        return ops.conv_gn(h, p["Conv_1"], gn=p["GroupNorm_0"])
 
     def decoder(self, z):
         cfg, p, ops = self.config, self.p["decoder"], self.ops
-        h = ops.conv(ops.prep(z), p["Conv_0"])
+        h = ops.conv_gn(z, p["Conv_0"], want_stats=True)
         h = ResnetBlock(ops, h, p["MidBlock_0"]["ResnetBlock_0"])
         h = ResnetBlock(ops, h, p["MidBlock_0"]["ResnetBlock_1"])
         for n, i in enumerate(reversed(range(cfg.num_resolutions))):
@@ -274,7 +331,7 @@ class VQGANModel:
                 h = ResnetBlock(ops, h, blk["ResnetBlock_%d" % j])
             if i != 0:
                 h = Upsample(ops, h, blk["Upsample_0"])
-        return ops.conv(ops.prep(h, p["GroupNorm_0"]), p["Conv_1"], clip=True)   # clip(-1,1): vqgan.py:141
+        return ops.conv_gn(h, p["Conv_1"], gn=p["GroupNorm_0"], clip=True)   # clip(-1,1): vqgan.py:141
 
     def encode(self, pixel_values):
         x = self._to_dev(pixel_values)
@@ -283,7 +340,7 @@ class VQGANModel:
             T = x.shape[1]
             x = x.reshape((-1,) + tuple(x.shape[2:]))
         h = self.encoder(x.contiguous())
-        h = self.ops.conv(self.ops.prep(h), self.p["quant_conv"])
+        h = self.ops.conv_gn(h, self.p["quant_conv"])
         zq, idx = VectorQuantizer(self.ops, h, self.p["quantize"])
         if T is not None:
             zq = zq.reshape((-1, T) + tuple(zq.shape[1:]))
@@ -297,7 +354,7 @@ class VQGANModel:
         if z.dim() == 5:
             T = z.shape[1]
             z = z.reshape((-1,) + tuple(z.shape[2:]))
-        h = self.ops.conv(self.ops.prep(z.contiguous()), self.p["post_quant_conv"])
+        h = self.ops.conv_gn(z.contiguous(), self.p["post_quant_conv"])
         y = self.decoder(h)
         if T is not None:
             y = y.reshape((-1, T) + tuple(y.shape[1:]))
@@ -314,7 +371,7 @@ class VQGAN:
     the reference) or an already loaded param tree. replicate=True shards the frame axis over the
     visible GPUs of this process group (the reference's jax.pmap); weights are replicated."""
 
-    def __init__(self, vqgan_checkpoint, replicate=False, precision="bf16x3", device=None):
+    def __init__(self, vqgan_checkpoint, replicate=False, precision="fp16x2", device=None):
         assert vqgan_checkpoint != '' and vqgan_checkpoint is not None
         self.replicate = replicate
         self.config = VQGANConfig.get_default_config()

@@ -27,7 +27,10 @@ class CpuVqOps:
             y = y.repeat_interleave(2, dim=1).repeat_interleave(2, dim=2)
         return F.pad(y, (0, cpad - C)), None          # zero channel padding, like the kernel's planes
 
-    def conv(self, planes, pc, stride=1, residual=None, clip=False):
+    def conv_gn(self, x, pc, gn=None, upsample=False, stride=1, residual=None, clip=False, want_stats=False):
+        return self.conv(self.prep(x, gn, upsample), pc, stride=stride, residual=residual, clip=clip)
+
+    def conv(self, planes, pc, stride=1, residual=None, clip=False, want_stats=False):
         a, _ = planes
         assert a.shape[-1] == pc.cpad, (a.shape, pc.cpad)
         w = (pc.w_hi.float() + pc.w_lo.float()).reshape(pc.k, pc.k, pc.cout_pad, pc.cpad)    # [ky][kx][Cout_pad][Cpad]

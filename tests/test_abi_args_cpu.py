@@ -36,7 +36,7 @@ BAD_CALLS = [
     ("lwm_ring_copy", (N, P, 16, N), ARG, "bad arguments"),
     ("lwm_ring_signal", (N, 0, 0, 1, N), ARG, "null context"),
     ("lwm_attn_bwd_prep", (P, P, P, 1, 2, 128, 96, N), SHAPE, "head_dim"),
-    ("lwm_attn_bwd_lse", (P, P, 0, N), ARG, "bad args"),
+    ("lwm_attn_bwd_lse", (P, P, 0, 0.0, N), ARG, "bad args"),
     ("lwm_attn_to_f16", (P, P, P, P, 12, N), SHAPE, "multiple of 8"),
     ("lwm_attn_decode_partial", (P, P, P, N, P, P, N, 1, 2, 1, 128, 128, 0, 0, 0, 4, 0.1, N), ARG, "null"),
     ("lwm_attn_decode_merge", (P, P, 0, P, P, 8, N), ARG, "bad args"),

@@ -146,14 +146,15 @@ def test_bwd_kv_split_additivity_large():
     assert rel_fro(to_np(dv2), to_np(dv)) < 1e-5
 
 
-def test_fp32_inputs_take_the_documented_cast_path():
-    """fp32 q/k/v (the dtype of the reference's scripts): one rounding to bf16 on entry, fp32 output and gradients;
-    must equal the bf16-input call on the pre-rounded tensors."""
+def test_fp32_inputs_take_the_documented_cast_path_in_bf16_mode():
+    """precision='bf16' (the legacy operand mode): fp32 q/k/v get one rounding to bf16 on entry, fp32 output and
+    gradients; must equal the bf16-input call on the pre-rounded tensors. (The default fp16 mode takes fp32 inputs
+    natively: tests/test_attn_public_op_gpu.py.)"""
     from lwm_b200.ringattention import ringattention
     q, k, v, do = make_qkv(1, 256, 256, 2, n_extra=1)
     q32, k32, v32 = [(t.float() + 1e-4).requires_grad_(True) for t in (q, k, v)]   # not exactly representable in bf16
     qb, kb, vb = [t.detach().to(torch.bfloat16).requires_grad_(True) for t in (q32, k32, v32)]
-    kw = dict(axis_name="sp", blockwise_kwargs=dict(causal_block_size=1))
+    kw = dict(axis_name="sp", blockwise_kwargs=dict(causal_block_size=1), precision="bf16")
     o32 = ringattention(q32, k32, v32, None, None, **kw)
     ob = ringattention(qb, kb, vb, None, None, **kw)
     o32.backward(do.float())

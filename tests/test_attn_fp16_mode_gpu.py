@@ -30,7 +30,7 @@ def _run(q, k, v, do, causal=True, bias=None, seg=None):
     ra.bwd_prep(out32, do, delta)      # fp16 mode keeps the un-rounded output as the residual for delta
     dq = torch.zeros(B, S, H, D, dtype=torch.float32, device="cuda")
     dk, dv = torch.zeros_like(dq), torch.zeros_like(dq)
-    ra.bwd_step(q16, k16, v16, d16, ra.lse_for_bwd(lse), delta, dq, dk, dv, 0, 0, causal, bias, seg, scales=(sq, sk, sv, sd))
+    ra.bwd_step(q16, k16, v16, d16, ra.lse_for_bwd(lse, f16=True), delta, dq, dk, dv, 0, 0, causal, bias, seg, scales=(sq, sk, sv, sd))
     torch.cuda.synchronize()
     o32 = to_np(acc_o) / to_np(acc_l).transpose(0, 2, 1)[..., None]
     return o32, to_np(out), to_np(lse), to_np(dq), to_np(dk), to_np(dv)

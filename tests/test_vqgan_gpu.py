@@ -1,10 +1,11 @@
 """GPU parity of the VQGAN tokenizer kernels against oracle/vqgan_ref.py (flax-semantics CPU
 restatement of lwm/vqgan.py).
 
-Tolerances: relative Frobenius error <= 1e-3 (north_star) for every float tensor in the default
-'bf16x3' precision mode (measured ~1e-5); codebook indices bit-exact at the VectorQuantizer op
-boundary (identical fp32 z in, pinned operation order) and >= 99.9 % identical end to end, with
-every mismatch confined to codes whose oracle distances tie to within float32 resolution."""
+Tolerances: relative Frobenius error <= 1e-3 (north_star) for every float tensor, in the default mixed
+'fp16x2' precision mode (measured 6e-4 .. 7e-4 end to end) and in 'bf16x3' (~1e-5); codebook indices bit-exact at the
+VectorQuantizer op boundary (identical fp32 z in, pinned operation order); end to end >= 99.9 % identical in 'bf16x3'
+(every mismatch a float32-resolution tie in the oracle's own distances) and >= 99 % in 'fp16x2' (every mismatch a
+near-tie within the latent's 1e-3 error)."""
 import numpy as np
 import pytest
 import torch
@@ -102,6 +103,68 @@ def test_downsample_upsample_cin3(vr):
     assert rel_fro(to_np(yi), vr.conv2d(xi, pi).numpy()) < 1e-5
 
 
+def _stats_of(y, groups=32):
+    N, H, W, C = y.shape
+    yg = y.double().reshape(N, H * W, groups, C // groups)
+    return torch.stack([yg.sum(dim=(1, 3)), (yg * yg).sum(dim=(1, 3))], dim=-1)       # [N, groups, 2]
+
+
+@pytest.mark.parametrize("cin,cout,k,H", [(128, 128, 3, 32), (128, 256, 3, 16), (256, 256, 3, 16), (128, 256, 1, 16),
+                                          (768, 64, 3, 16), (64, 64, 1, 16), (64, 768, 3, 16), (512, 768, 3, 16),
+                                          (128, 3, 3, 32)])
+def test_conv_fp16x2_scheme(vr, cin, cout, k, H):
+    """one fp16 activation plane x stacked fp16 hi|lo weights: exact up to the activation's rounding to fp16, and the
+    epilogue's GroupNorm statistics of the output"""
+    g = torch.Generator().manual_seed(cin * 7 + cout)
+    x = torch.randn(2, H, H, cin, generator=g) * 1.3
+    p = vr._conv_p(g, k, cin, cout)
+    ops = _ops("fp16x2")
+    want_stats = cout % 128 == 0
+    y = ops.conv(ops.prep(x.cuda(), n_pass=2), _pc(p), want_stats=want_stats)
+    torch.cuda.synchronize()
+    pd = {"kernel": p["kernel"].double(), "bias": p["bias"].double()}
+    ref = vr.conv2d(x.double(), pd)
+    ref16 = vr.conv2d(x.to(torch.float16).double(), pd)          # the same operand rounding on the CPU
+    assert rel_fro(to_np(y), ref16.numpy()) < 2e-5
+    assert rel_fro(to_np(y), ref.numpy()) < 6e-4
+    if want_stats:
+        st = y._gn_stats.cpu()
+        ref_st = _stats_of(y.cpu())
+        assert float((st - ref_st).abs().max() / ref_st.abs().max()) < 1e-5
+    else:
+        assert not hasattr(y, "_gn_stats")
+
+
+def test_prep_fp16_plane_and_upsample(vr):
+    g = torch.Generator().manual_seed(21)
+    x = torch.randn(2, 16, 16, 256, generator=g) * 1.7 + 0.3
+    p = vr._gn_p(g, 256)
+    ops = _ops("fp16x2")
+    hi, lo = ops.prep(x.cuda(), _gn(p), upsample=True)
+    assert lo is None and hi.dtype == torch.float16 and tuple(hi.shape) == (2, 32, 32, 256)
+    ref = vr.silu(vr.group_norm(x, p)).repeat_interleave(2, dim=1).repeat_interleave(2, dim=2)
+    assert rel_fro(to_np(hi), ref.numpy()) < 3e-4          # fp16: 11 significant bits
+
+
+def test_resnet_block_fp16x2_uses_epilogue_statistics(vr):
+    from lwm_b200 import vqgan as V
+    g = torch.Generator().manual_seed(6)
+    x = torch.randn(2, 64, 64, 128, generator=g)
+    p = vr._resnet_p(g, 128, 256)
+    packed = V._pack_tree(p, torch.device("cuda"))
+    ops = _ops("fp16x2")
+    calls = []
+    orig = ops.gn_stats
+    ops.gn_stats = lambda t: (calls.append(1), orig(t))[1]
+    y = V.ResnetBlock(ops, x.cuda(), packed)
+    assert len(calls) == 1                  # only the block input needs the stand-alone pass; GroupNorm_1 reads Conv_0's epilogue
+    assert hasattr(y, "_gn_stats")
+    assert rel_fro(to_np(y), vr.resnet_block(x, p).numpy()) < 6e-4
+    st = y._gn_stats.cpu()
+    ref_st = _stats_of(y.cpu())
+    assert float((st - ref_st).abs().max() / ref_st.abs().max()) < 1e-5
+
+
 def test_resnet_block(vr):
     from lwm_b200 import vqgan as V
     g = torch.Generator().manual_seed(6)
@@ -109,7 +172,7 @@ def test_resnet_block(vr):
     p = vr._resnet_p(g, 128, 256)
     packed = V._pack_tree(p, torch.device("cuda"))
     y = V.ResnetBlock(_ops(), x.cuda(), packed)
-    assert rel_fro(to_np(y), vr.resnet_block(x, p).numpy()) < TOL
+    assert rel_fro(to_np(y), vr.resnet_block(x, p).numpy()) < 1e-4
 
 
 @pytest.mark.parametrize("codebook", ["normal", "uniform"])
@@ -130,20 +193,55 @@ def test_vq_argmin_bit_exact(vr, codebook):
     assert np.array_equal(back.cpu().numpy(), emb.numpy()[ref_idx])
 
 
+def test_encode_end_to_end_default_mode(vr):
+    """the default mixed 'fp16x2' mode: latents within 1e-3, codes identical except near-ties"""
+    from lwm_b200.vqgan import VQGAN
+    params = vr.init_params(seed=0, codebook="normal")
+    g = torch.Generator().manual_seed(11)
+    x = torch.rand(1, 2, 256, 256, 3, generator=g) * 2 - 1
+    tok = VQGAN(params)
+    assert tok.model.ops.n_pass == 2
+    zq, idx = tok.encode(x)
+    torch.cuda.synchronize()
+    ref_zq, ref_idx, ref_h = vr.encode(x, params)
+    h = tok.model.ops.conv_gn(tok.model.encoder(x.reshape(2, 256, 256, 3).cuda()), tok.model.p["quant_conv"])
+    err = rel_fro(to_np(h), ref_h)
+    print("fp16x2 encode latent rel err %.2e" % err)
+    assert err < TOL
+    got = to_np(idx).astype(np.int32)
+    assert (got == ref_idx).mean() >= 0.99
+    emb = params["quantize"]["embeddings"].numpy()
+    for b in np.argwhere(got != ref_idx):
+        zrow = ref_h.reshape(-1, 64)[np.ravel_multi_index(tuple(b[1:]), (2, 16, 16))][None]
+        d = vr.vq_distances_f32(zrow, emb)[0]
+        assert abs(d[got[tuple(b)]] - d[ref_idx[tuple(b)]]) <= 4e-3 * abs(d.min())     # a near-tie at the latent's accuracy
+
+
+def test_decode_end_to_end_default_mode(vr):
+    from lwm_b200.vqgan import VQGAN
+    params = vr.init_params(seed=1, codebook="normal")
+    g = torch.Generator().manual_seed(12)
+    codes = torch.randint(0, 8192, (1, 16, 16), generator=g)
+    y = VQGAN(params).decode(codes)
+    torch.cuda.synchronize()
+    err = rel_fro(to_np(y), vr.decode(codes.numpy(), params))
+    print("fp16x2 decode rel err %.2e" % err)
+    assert float(y.abs().max()) <= 1.0 and err < TOL
+
+
 def test_encode_end_to_end(vr):
     from lwm_b200.vqgan import VQGAN
     params = vr.init_params(seed=0, codebook="normal")
     g = torch.Generator().manual_seed(11)
     x = torch.rand(1, 2, 256, 256, 3, generator=g) * 2 - 1      # [B,T,H,W,C] video input
-    tok = VQGAN(params)
+    tok = VQGAN(params, precision="bf16x3")
     zq, idx = tok.encode(x)
     torch.cuda.synchronize()
     assert tuple(zq.shape) == (1, 2, 16, 16, 64) and tuple(idx.shape) == (1, 2, 16, 16)
     ref_zq, ref_idx, ref_h = vr.encode(x, params)
     # pre-quantisation latent: the float parity statement
-    h = tok.model.ops.conv(tok.model.ops.prep(tok.model.encoder(x.reshape(2, 256, 256, 3).cuda())),
-                           tok.model.p["quant_conv"])
-    assert rel_fro(to_np(h), ref_h) < TOL
+    h = tok.model.ops.conv_gn(tok.model.encoder(x.reshape(2, 256, 256, 3).cuda()), tok.model.p["quant_conv"])
+    assert rel_fro(to_np(h), ref_h) < 1e-4
     got = to_np(idx).astype(np.int32)
     agree = (got == ref_idx).mean()
     assert agree >= 0.999, agree
@@ -161,10 +259,10 @@ def test_decode_end_to_end(vr):
     params = vr.init_params(seed=1, codebook="normal")
     g = torch.Generator().manual_seed(12)
     codes = torch.randint(0, 8192, (1, 16, 16), generator=g)
-    tok = VQGAN(params)
+    tok = VQGAN(params, precision="bf16x3")
     y = tok.decode(codes)
     torch.cuda.synchronize()
     ref = vr.decode(codes.numpy(), params)
     assert tuple(y.shape) == (1, 256, 256, 3)
     assert float(y.abs().max()) <= 1.0
-    assert rel_fro(to_np(y), ref) < TOL
+    assert rel_fro(to_np(y), ref) < 1e-4
