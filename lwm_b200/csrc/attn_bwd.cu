@@ -530,6 +530,10 @@ static int attn_bwd_launch(const void* q, const void* k, const void* v, const vo
     return lwm_fail(LWM_ERR_ARG, "attn_bwd: null pointer");
   if (q_pos0 + Sq > 0x7fffffffLL || k_pos0 + Sk > 0x7fffffffLL)
     return lwm_fail(LWM_ERR_SHAPE, "attn_bwd: global positions must fit in int32");
+  if (bias && bias_stride < k_pos0 + Sk)
+    return lwm_fail(LWM_ERR_SHAPE, "attn_bwd: bias is indexed by GLOBAL key position: bias_stride < k_pos0 + Sk");
+  if (segment_ids && (seg_stride < q_pos0 + Sq || seg_stride < k_pos0 + Sk))
+    return lwm_fail(LWM_ERR_SHAPE, "attn_bwd: segment_ids is indexed by GLOBAL position: seg_stride < max(q_pos0 + Sq, k_pos0 + Sk)");
   if (!lwm_check_device()) return LWM_ERR_DEVICE;
   CUtensorMap tq, tk, tv, tdo, tdq;
   if (!make_bf16_tmap(&tq, q, B, Sq, H) || !make_bf16_tmap(&tk, k, B, Sk, H) || !make_bf16_tmap(&tv, v, B, Sk, H) ||
@@ -546,7 +550,10 @@ static int attn_bwd_launch(const void* q, const void* k, const void* v, const vo
   p.prof = lwm_prof_buffer();
   p.scale_q = scale_q; p.scale_k = scale_k; p.scale_v = scale_v; p.scale_do = scale_do;
   p.dkv_init = dkv_init ? 1 : 0;
-  static bool attr_set = false;
+  static bool attr_set_dev[64] = {};
+  int cur_dev = 0;
+  cudaGetDevice(&cur_dev);
+  bool& attr_set = attr_set_dev[cur_dev & 63];      // function attributes are per device
   if (!attr_set) {
     if (cudaFuncSetAttribute(attn_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmemBytes) !=
             cudaSuccess ||

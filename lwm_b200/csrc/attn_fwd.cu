@@ -429,6 +429,10 @@ static int attn_fwd_launch(const void* q, const void* k, const void* v, void* ou
     return lwm_fail(LWM_ERR_ARG, "attn_fwd: carry buffers required unless first && last");
   if (q_pos0 + Sq > 0x7fffffffLL || k_pos0 + Sk > 0x7fffffffLL)
     return lwm_fail(LWM_ERR_SHAPE, "attn_fwd: global positions must fit in int32");
+  if (bias && bias_stride < k_pos0 + Sk)
+    return lwm_fail(LWM_ERR_SHAPE, "attn_fwd: bias is indexed by GLOBAL key position: bias_stride < k_pos0 + Sk");
+  if (segment_ids && (seg_stride < q_pos0 + Sq || seg_stride < k_pos0 + Sk))
+    return lwm_fail(LWM_ERR_SHAPE, "attn_fwd: segment_ids is indexed by GLOBAL position: seg_stride < max(q_pos0 + Sq, k_pos0 + Sk)");
   if (!lwm_check_device()) return LWM_ERR_DEVICE;
   CUtensorMap tq, tk, tv;
   if (!make_qkv_tmap(&tq, q, B, Sq, H) || !make_qkv_tmap(&tk, k, B, Sk, H) || !make_qkv_tmap(&tv, v, B, Sk, H))
@@ -445,7 +449,10 @@ static int attn_fwd_launch(const void* q, const void* k, const void* v, void* ou
   p.prof = lwm_prof_buffer();
   p.scale_q = scale_q; p.scale_k = scale_k; p.scale_v = scale_v;
   p.out_f32 = out_f32;
-  static bool attr_set = false;
+  static bool attr_set_dev[64] = {};
+  int cur_dev = 0;
+  cudaGetDevice(&cur_dev);
+  bool& attr_set = attr_set_dev[cur_dev & 63];      // function attributes are per device
   if (!attr_set) {
     if (cudaFuncSetAttribute(attn_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmemBytes) !=
             cudaSuccess ||

@@ -96,9 +96,14 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constan
   tc_fence_after();
   const uint32_t tmem = *tmem_base_s;
 
+  // every CTA owns a CONTIGUOUS range of tiles, ordered N-tile-major then image-major: consecutive tiles share the
+  // activation halo in L2, and (image, N tile) — the key of the GroupNorm-statistics accumulators — changes at most a
+  // few times per CTA
+  const int tile_begin = int((long long)total_tiles * blockIdx.x / gridDim.x);
+  const int tile_end = int((long long)total_tiles * (blockIdx.x + 1) / gridDim.x);
   auto decode_tile = [&](int tile, int& n, int& oh0, int& ow0, int& nt) {
-    nt = tile % p.n_tiles;
-    int m = tile / p.n_tiles;
+    nt = tile / m_tiles;
+    int m = tile % m_tiles;
     ow0 = (m % tiles_w) * 16;
     m /= tiles_w;
     oh0 = (m % tiles_h) * 8;
@@ -109,7 +114,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constan
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
       int it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = tile_begin; tile < tile_end; ++tile) {
         int n, oh0, ow0, nt;
         decode_tile(tile, n, oh0, ow0, nt);
         for (int ki = 0; ki < k_iters; ++ki, ++it) {
@@ -138,7 +143,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constan
       const uint32_t idesc = p.n_pass == 2 ? make_idesc(128, 2 * p.BN, false, false, kFmtF16, kFmtF16)
                                            : make_idesc_bf16(128, p.BN, false, false);
       int it = 0, local = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
+      for (int tile = tile_begin; tile < tile_end; ++tile, ++local) {
         const int acc = local & 1;
         mbar_wait(&tmem_empty[acc], ((local >> 1) & 1) ^ 1);
         tc_fence_after();
@@ -171,9 +176,48 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constan
     const int r = threadIdx.x;  // TMEM lane = pixel inside the 8x16 tile
     const uint32_t lane_off = uint32_t(warp * 32) << 16;
     int local = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
+    // GroupNorm statistics of the output: per-thread (= per-pixel-slot) running sums for every channel quad of the
+    // current N tile, kept in registers across tiles and folded (warp shuffle -> shared -> double atomics) only when
+    // the (image, N tile) pair changes — a handful of times per CTA thanks to the contiguous tile ranges.
+    float st1[32], st2[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) st1[i] = st2[i] = 0.f;
+    int st_n = -1, st_nt = -1;
+    const int cpg = p.stats ? p.Cout / p.groups : 1;
+    auto flush_stats = [&]() {
+      if (st_n < 0) return;
+#pragma unroll
+      for (int qd = 0; qd < 32; ++qd) {
+        if (qd * 4 >= p.BN) break;
+        float s1 = st1[qd], s2 = st2[qd];
+#pragma unroll
+        for (int sh = 16; sh > 0; sh >>= 1) {
+          s1 += __shfl_xor_sync(0xffffffffu, s1, sh);
+          s2 += __shfl_xor_sync(0xffffffffu, s2, sh);
+        }
+        const int c = st_nt * p.BN + qd * 4;
+        if (lane == 0 && c < p.Cout) {
+          atomicAdd(&s_stats[2 * (c / cpg)], s1);
+          atomicAdd(&s_stats[2 * (c / cpg) + 1], s2);
+        }
+        st1[qd] = st2[qd] = 0.f;
+      }
+      named_bar_sync(2, 128);
+      if (r < 2 * p.groups) {
+        const float t = s_stats[r];
+        if (t != 0.f) atomicAdd(&p.stats[(size_t)st_n * p.groups * 2 + r], (double)t);
+        s_stats[r] = 0.f;
+      }
+      named_bar_sync(2, 128);
+    };
+    for (int tile = tile_begin; tile < tile_end; ++tile, ++local) {
       int n, oh0, ow0, nt;
       decode_tile(tile, n, oh0, ow0, nt);
+      if (p.stats && (n != st_n || nt != st_nt)) {
+        flush_stats();
+        st_n = n;
+        st_nt = nt;
+      }
       const int acc = local & 1;
       mbar_wait(&tmem_full[acc], (local >> 1) & 1);
       tc_fence_after();
@@ -181,8 +225,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constan
       float* dst = p.out + pix * p.Cout;
       const float* res = p.residual ? p.residual + pix * p.Cout : nullptr;
       const int c_base = nt * p.BN;
-      const int cpg = p.stats ? p.Cout / p.groups : 1;
-      for (int c0 = 0; c0 < p.BN; c0 += 16) {
+#pragma unroll
+      for (int ci = 0; ci < 16; ++ci) {
+        const int c0 = ci * 16;
+        if (c0 >= p.BN) break;
         uint32_t v[16];
         tmem_ld_x16(tmem + lane_off + acc * 256 + c0, v);
         if (p.n_pass == 2) {
@@ -211,19 +257,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constan
               o.z = fminf(fmaxf(o.z, -1.f), 1.f); o.w = fminf(fmaxf(o.w, -1.f), 1.f);
             }
             *reinterpret_cast<float4*>(dst + c + j) = o;
-            if (p.stats) {   // a channel quad never straddles a group (C/groups % 4 == 0): reduce it over the warp's pixels
-              float s1 = (o.x + o.y) + (o.z + o.w);
-              float s2 = (o.x * o.x + o.y * o.y) + (o.z * o.z + o.w * o.w);
-#pragma unroll
-              for (int sh = 16; sh > 0; sh >>= 1) {
-                s1 += __shfl_xor_sync(0xffffffffu, s1, sh);
-                s2 += __shfl_xor_sync(0xffffffffu, s2, sh);
-              }
-              if (lane == 0) {
-                const int g = (c + j) / cpg;
-                atomicAdd(&s_stats[2 * g], s1);
-                atomicAdd(&s_stats[2 * g + 1], s2);
-              }
+            if (p.stats && ci < 8) {   // stats need BN <= 128 (checked on the host); a quad never straddles a group
+              st1[ci * 4 + j / 4] += (o.x + o.y) + (o.z + o.w);
+              st2[ci * 4 + j / 4] += (o.x * o.x + o.y * o.y) + (o.z * o.z + o.w * o.w);
             }
           }
         } else {
@@ -237,18 +273,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constan
             }
         }
       }
-      if (p.stats) {   // flush this tile's per-group partials (fp32 over 128 pixels) into the double accumulators
-        named_bar_sync(2, 128);
-        if (r < 2 * p.groups) {
-          const float t = s_stats[r];
-          if (t != 0.f) atomicAdd(&p.stats[(size_t)n * p.groups * 2 + r], (double)t);
-          s_stats[r] = 0.f;
-        }
-        named_bar_sync(2, 128);
-      }
       tc_fence_before();
       mbar_arrive(&tmem_empty[acc]);
     }
+    if (p.stats) flush_stats();
   }
   tc_fence_before();
   __syncthreads();
@@ -271,6 +299,8 @@ static int conv_launch(const void* a_hi, const void* a_lo, const void* w_hi, con
   if ((ksize != 1 && ksize != 3) || (stride != 1 && stride != 2)) return lwm_fail(LWM_ERR_SHAPE, "vq_conv2d: ksize 1|3, stride 1|2");
   if (stats && (groups <= 0 || groups > 64 || Cout % groups || (Cout / groups) % 4 || Cout % 16))
     return lwm_fail(LWM_ERR_SHAPE, "vq_conv2d: output statistics need Cout % 16 == 0 and (Cout/groups) % 4 == 0, groups <= 64");
+  if (stats && n_pass != 2)
+    return lwm_fail(LWM_ERR_ARG, "vq_conv2d: output statistics are an epilogue of the fp16x2 scheme (N tile <= 128)");
   if (!lwm_check_device()) return LWM_ERR_DEVICE;
   int BN = Cout_pad;
   if (n_pass == 2) {      // fp16x2 stacks hi|lo: the UMMA is 2*BN wide -> BN = largest multiple of 16 <= 128 dividing Cout_pad
@@ -320,14 +350,14 @@ static int conv_launch(const void* a_hi, const void* a_lo, const void* w_hi, con
   if (stages < 2) return lwm_fail(LWM_ERR_SHAPE, "vq_conv2d: tile does not fit in shared memory");
   p.stages = stages;
   const int smem_bytes = stages * stage_bytes + 1024;
-  static int max_set = 0;
-  if (smem_bytes > max_set) {
-    if (cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
-      return lwm_fail(LWM_ERR_CUDA, "vq_conv2d: cannot raise dynamic shared memory limit");
-    max_set = 227 * 1024;
-  }
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
+  static bool attr_set_dev[64] = {};      // function attributes are per device
+  if (!attr_set_dev[dev & 63]) {
+    if (cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
+      return lwm_fail(LWM_ERR_CUDA, "vq_conv2d: cannot raise dynamic shared memory limit");
+    attr_set_dev[dev & 63] = true;
+  }
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int total_tiles = N * (Ho / 8) * (Wo / 16) * p.n_tiles;
   const int grid = total_tiles < sms ? total_tiles : sms;

@@ -57,12 +57,26 @@ __global__ void prep_kernel(const float* __restrict__ x, const double* __restric
                             const float* __restrict__ gamma, const float* __restrict__ beta,
                             __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int N, int H, int W,
                             int C, int C_pad, int groups, int up, float eps, int write_lo) {
-  // one thread = 8 channels of one output pixel: 2 x 16 B loads, 16 B stores per plane
+  // one thread = 8 channels of one output pixel: 2 x 16 B loads, 16 B stores per plane.
+  // (mean, rstd) of every (sample, group) are derived once per block from the float64 sums into shared memory: the
+  // element loop is then pure fp32 (FFMA + 2 MUFU per element), no float64 arithmetic per quad.
+  extern __shared__ float s_mr[];    // [N*groups][2]
   const int Ho = H << up, Wo = W << up;
   const int octs = C_pad / 8;
   const size_t total = (size_t)N * Ho * Wo * octs;
-  const int cpg = C / groups;
-  const double inv_cnt = 1.0 / ((double)H * W * cpg);
+  const int cpg = stats ? C / groups : 1;
+  if (stats) {
+    const double inv_cnt = 1.0 / ((double)H * W * cpg);
+    for (int i = threadIdx.x; i < N * groups; i += blockDim.x) {
+      const float mean = float(stats[2 * i] * inv_cnt);
+      float var = float(stats[2 * i + 1] * inv_cnt) - mean * mean;   // flax fast variance, clamped at 0
+      var = fmaxf(var, 0.f);
+      s_mr[2 * i] = mean;
+      s_mr[2 * i + 1] = rsqrtf(var + eps);
+    }
+    __syncthreads();
+  }
+#pragma unroll 2
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const int o8 = int(i % octs);
     size_t pix = i / octs;
@@ -82,18 +96,14 @@ __global__ void prep_kernel(const float* __restrict__ x, const double* __restric
         yy[0] = v.x; yy[1] = v.y; yy[2] = v.z; yy[3] = v.w;
         if (stats) {
           const int g = c / cpg;
-          const double sum = stats[((size_t)n * groups + g) * 2], sumsq = stats[((size_t)n * groups + g) * 2 + 1];
-          const float mean = float(sum * inv_cnt);
-          float var = float(sumsq * inv_cnt) - mean * mean;   // flax fast variance, clamped at 0
-          var = fmaxf(var, 0.f);
-          const float rstd = rsqrtf(var + eps);
+          const float mean = s_mr[2 * (n * groups + g)], rstd = s_mr[2 * (n * groups + g) + 1];
           const float4 g4 = *reinterpret_cast<const float4*>(gamma + c);
           const float4 b4 = *reinterpret_cast<const float4*>(beta + c);
           const float gg[4] = {g4.x, g4.y, g4.z, g4.w}, bb[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const float t = (yy[e] - mean) * rstd * gg[e] + bb[e];
-            yy[e] = t / (1.0f + __expf(-t));   // silu = t * sigmoid(t)
+            yy[e] = __fdividef(t, 1.0f + __expf(-t));   // silu = t * sigmoid(t)
           }
         }
       }
@@ -319,12 +329,13 @@ extern "C" int lwm_vq_prep(const float* x, const double* gn_stats, const float* 
   if (C % 4 || C_pad % 8 || C_pad < C) return lwm_fail(LWM_ERR_SHAPE, "vq_prep: C % 4 and C_pad % 8 required");
   if (gn_stats && (!gamma || !beta || C % groups || (C / groups) % 4))
     return lwm_fail(LWM_ERR_SHAPE, "vq_prep: GroupNorm needs gamma/beta and C/groups % 4 == 0");
+  if (gn_stats && (size_t)N * groups * 8 > 40 * 1024) return lwm_fail(LWM_ERR_SHAPE, "vq_prep: N * groups too large (<= 5120)");
   if (!lwm_check_device()) return LWM_ERR_DEVICE;
   const size_t total = (size_t)N * (H << upsample2x) * (W << upsample2x) * (C_pad / 8);
   const int threads = 256;
   const size_t want = (total + threads - 1) / threads;
   const unsigned blocks = unsigned(want < 148u * 32 ? want : 148u * 32);
-  prep_kernel<false><<<blocks, threads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  prep_kernel<false><<<blocks, threads, gn_stats ? size_t(N) * groups * 8 : 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       x, gn_stats, gamma, beta, reinterpret_cast<__nv_bfloat16*>(hi), reinterpret_cast<__nv_bfloat16*>(lo), N, H, W,
       C, C_pad, groups, upsample2x ? 1 : 0, eps, lo != nullptr);
   return lwm_check_launch("prep_kernel");
@@ -338,12 +349,13 @@ extern "C" int lwm_vq_prep_f16(const float* x, const double* gn_stats, const flo
   if (C % 4 || C_pad % 8 || C_pad < C) return lwm_fail(LWM_ERR_SHAPE, "vq_prep_f16: C % 4 and C_pad % 8 required");
   if (gn_stats && (!gamma || !beta || C % groups || (C / groups) % 4))
     return lwm_fail(LWM_ERR_SHAPE, "vq_prep_f16: GroupNorm needs gamma/beta and C/groups % 4 == 0");
+  if (gn_stats && (size_t)N * groups * 8 > 40 * 1024) return lwm_fail(LWM_ERR_SHAPE, "vq_prep_f16: N * groups too large (<= 5120)");
   if (!lwm_check_device()) return LWM_ERR_DEVICE;
   const size_t total = (size_t)N * (H << upsample2x) * (W << upsample2x) * (C_pad / 8);
   const int threads = 256;
   const size_t want = (total + threads - 1) / threads;
   const unsigned blocks = unsigned(want < 148u * 32 ? want : 148u * 32);
-  prep_kernel<true><<<blocks, threads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  prep_kernel<true><<<blocks, threads, gn_stats ? size_t(N) * groups * 8 : 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       x, gn_stats, gamma, beta, reinterpret_cast<__nv_bfloat16*>(out), nullptr, N, H, W, C, C_pad, groups,
       upsample2x ? 1 : 0, eps, 0);
   return lwm_check_launch("prep_kernel<f16>");

@@ -49,22 +49,22 @@ class _Span:
 
 
 def _high_priority_group(group, channel=0):
-    """A clone of `group` whose NCCL kernels run on HIGH-PRIORITY streams (created once, collectively).
+    """A clone of `group` whose NCCL kernels run on HIGH-PRIORITY streams (created once per (group, channel)).
     The attention tile kernels occupy every SM (1 CTA/SM, all of the register file and shared memory), and
     ProcessGroupNCCL's default streams have normal priority: its send/recv kernels then only get SMs when an
     attention grid drains, i.e. the K/V prefetch does not overlap at all (measured: 83 ms/step at 8 GPUs vs
     63 ms for the same per-rank work without communication). With priority the copy CTAs are placed as soon
-    as any attention CTA retires (~0.2 ms)."""
+    as any attention CTA retires (~0.2 ms).
+    The clone is made with use_local_synchronization=True: only the MEMBERS of `group` take part, so an 'sp' axis that
+    is a proper subgroup of WORLD (dp x sp meshes) can create its clone inside its first forward without the other
+    subgroups calling new_group with the same arguments. $LWM_RING_HP_GROUP=0 keeps the caller's group."""
     key = (id(group) if group is not None else 0, channel)
     if key not in _HP_GROUPS:
         hp = group
-        try:
-            if dist.get_backend(group) == "nccl":
-                opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
-                ranks = dist.get_process_group_ranks(group if group is not None else dist.group.WORLD)
-                hp = dist.new_group(ranks=ranks, backend="nccl", pg_options=opts)
-        except Exception:       # older torch / non-NCCL backends: keep the caller's group
-            hp = group
+        if os.environ.get("LWM_RING_HP_GROUP", "1") != "0" and dist.get_backend(group) == "nccl":
+            opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
+            ranks = dist.get_process_group_ranks(group if group is not None else dist.group.WORLD)
+            hp = dist.new_group(ranks=ranks, backend="nccl", pg_options=opts, use_local_synchronization=True)
         _HP_GROUPS[key] = hp
     return _HP_GROUPS[key]
 

@@ -18,9 +18,13 @@ def select_frames(n_frames, max_n_frames):
     return None
 
 
-def frame_tokens(codes, max_n_frames=-1, eof_token=EOF_TOKEN, eov_token=EOV_TOKEN):
+def frame_tokens(codes, max_n_frames=-1, eof_token=EOF_TOKEN, eov_token=EOV_TOKEN, eov_every_frame=False):
     """codes int32 [T,16,16] / [T,P] (one clip) or [B,T,16,16] / [B,T,P] -> tokens int32 [B?, T'*(P+1)]: every frame's
-    codes then eof_token, eov_token after the last frame (vision_chat.py:97-104, data.py:206-212)."""
+    codes then eof_token, eov_token after the clip's last frame — the training data format (data.py:206-212).
+    eov_every_frame=True reproduces the stream lwm/vision_chat.py:91-107 actually feeds the model: it encodes ONE frame
+    per call (B = 1), so its `t == len(enc) - 1` test is true for every frame and 8193 follows each of them."""
+    if eov_every_frame:
+        eof_token = eov_token
     if not codes.is_cuda:
         raise _lib.LwmError("frame_tokens: codes must be a CUDA tensor (no CPU path)")
     c = codes.to(torch.int32)

@@ -367,13 +367,16 @@ class VQGANModel:
 
 
 class VQGAN:
-    """Drop-in for lwm/vqgan.py:14-56. `vqgan_checkpoint` is a path to the pickled flax params (as in
-    the reference) or an already loaded param tree. replicate=True shards the frame axis over the
-    visible GPUs of this process group (the reference's jax.pmap); weights are replicated."""
+    """Drop-in for lwm/vqgan.py:14-56. `vqgan_checkpoint` is a path to the pickled flax params (as in the reference) or
+    an already loaded param tree. replicate=True is the reference's `jax.pmap` branch (vqgan.py:20-28) in the
+    process-per-GPU model: the LEADING axis of the argument is mapped over the ranks of `group` (default WORLD) —
+    rank r computes slice [r] with its replicated weights and the per-rank results are all-gathered, so every rank
+    returns the full [n_ranks, ...] result, like pmap's output. Frames are independent: no other collective."""
 
-    def __init__(self, vqgan_checkpoint, replicate=False, precision="fp16x2", device=None):
+    def __init__(self, vqgan_checkpoint, replicate=False, precision="fp16x2", device=None, group=None):
         assert vqgan_checkpoint != '' and vqgan_checkpoint is not None
         self.replicate = replicate
+        self.group = group
         self.config = VQGANConfig.get_default_config()
         if isinstance(vqgan_checkpoint, (str, bytes)):
             with open(vqgan_checkpoint, "rb") as f:
@@ -384,8 +387,35 @@ class VQGAN:
             device = "cuda:%d" % torch.cuda.current_device() if torch.cuda.is_available() else "cuda"
         self.model = VQGANModel(self.config, self.params, device, precision)
 
+    def _pmap(self, fn, x):
+        import torch.distributed as dist
+        world, rank = 1, 0
+        if dist.is_available() and dist.is_initialized():
+            world, rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        x = torch.as_tensor(np.asarray(x) if not torch.is_tensor(x) else x)
+        if x.shape[0] != world:
+            raise ValueError("replicate=True maps the leading axis over the %d rank(s) of the group (jax.pmap semantics, "
+                             "lwm/vqgan.py:27-28): got leading axis %d" % (world, x.shape[0]))
+        outs = fn(x[rank])
+        single = not isinstance(outs, tuple)
+        outs = (outs,) if single else outs
+        full = []
+        for o in outs:
+            o = o.contiguous()
+            if world == 1:
+                full.append(o[None])
+                continue
+            g = torch.empty((world * o.shape[0],) + tuple(o.shape[1:]), dtype=o.dtype, device=o.device)
+            dist.all_gather_into_tensor(g, o, group=self.group)      # concatenated along dim 0 (gloo and NCCL agree)
+            full.append(g.view((world,) + tuple(o.shape)))
+        return full[0] if single else tuple(full)
+
     def encode(self, pixel_values):
+        if self.replicate:
+            return self._pmap(self.model.encode, pixel_values)
         return self.model.encode(pixel_values)
 
     def decode(self, encoding):
+        if self.replicate:
+            return self._pmap(self.model.decode, encoding)
         return self.model.decode(encoding)

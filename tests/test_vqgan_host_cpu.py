@@ -58,3 +58,72 @@ def test_packed_conv_layout_and_padding():
     for ky in range(3):
         for kx in range(3):
             assert torch.allclose(full[ky * 3 + kx, :40, :96], w[ky, kx].T, rtol=0, atol=2.0 ** -15 * float(w.abs().max()))
+
+
+def test_packed_conv_stacked_fp16_weights():
+    """fp16x2 scheme: [tap][Cout_pad/BN][hi rows | lo rows][Cpad], (hi + lo) * w_scale_inv reproduces the fp32 kernel"""
+    from lwm_b200.vqgan import PackedConv
+    g = torch.Generator().manual_seed(1)
+    for cin, cout in ((96, 40), (128, 256), (64, 768)):
+        w = torch.randn(3, 3, cin, cout, generator=g) * 0.03
+        pc = PackedConv({"kernel": w, "bias": torch.zeros(cout)}, torch.device("cpu"))
+        nt = pc.cout_pad // pc.bn
+        assert pc.cout_pad % pc.bn == 0 and pc.bn % 16 == 0 and pc.bn <= 128
+        assert tuple(pc.w_stack.shape) == (9, nt, 2 * pc.bn, pc.cpad) and pc.w_stack.dtype == torch.float16
+        hi, lo = pc.w_stack[:, :, :pc.bn].float(), pc.w_stack[:, :, pc.bn:].float()
+        assert float(hi.abs().max()) < 8192.0 * 1.01 and float(hi.abs().max()) >= 4096.0     # |w|max lands in [2^12, 2^13)
+        full = ((hi + lo) * pc.w_scale_inv).reshape(9, pc.cout_pad, pc.cpad)
+        for ky in range(3):
+            for kx in range(3):
+                assert torch.allclose(full[ky * 3 + kx, :cout, :cin], w[ky, kx].T, rtol=0,
+                                      atol=2.0 ** -20 * float(w.abs().max()))
+        assert torch.all(full[:, cout:, :] == 0) and torch.all(full[:, :, cin:] == 0)
+
+
+def _replicate_worker(rank, world, port, ret):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from lwm_b200.vqgan import VQGAN
+        from oracle import vqgan_ref as vr
+        from oracle.vq_step_ops import CpuVqOps
+        gold = np.load(os.path.join(GOLD, "vqgan_reference_small.npz"))
+        cfgd = dict(resolution=int(gold["cfg_resolution"]), hidden_channels=int(gold["cfg_hidden"]),
+                    num_embeddings=int(gold["cfg_codes"]))
+        params = vr.init_params(cfgd, seed=int(gold["param_seed"]), codebook="normal")
+        from lwm_b200.vqgan import VQGANConfig, VQGANModel
+        tok = VQGAN.__new__(VQGAN)
+        tok.replicate, tok.group = True, None
+        tok.model = VQGANModel(VQGANConfig.get_default_config(cfgd), params, device="cpu")
+        tok.model.ops = CpuVqOps()
+        tok.model._to_dev = lambda x: torch.as_tensor(np.asarray(x)).float()
+        px = torch.as_tensor(gold["pixels"]).reshape(2, 1, 64, 64, 3)         # leading axis = 2 ranks, one frame each
+        zq, idx = tok.encode(px)
+        ret[rank] = (tuple(idx.shape), idx.numpy().reshape(-1).tolist())
+        try:
+            tok.encode(px[:1])
+            ret["raised_%d" % rank] = False
+        except ValueError:
+            ret["raised_%d" % rank] = True
+    finally:
+        dist.destroy_process_group()
+
+
+def test_replicate_maps_the_leading_axis_over_ranks():
+    """VQGAN(replicate=True): the reference's jax.pmap branch (lwm/vqgan.py:20-28) over a 2-rank gloo group"""
+    import socket
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ret = mp.Manager().dict()
+    mp.spawn(_replicate_worker, args=(2, port, ret), nprocs=2, join=True)
+    gold = np.load(os.path.join(GOLD, "vqgan_reference_small.npz"))
+    for r in range(2):
+        shape, flat = ret[r]
+        assert shape == (2, 1) + tuple(gold["idx"].shape[-2:])
+        assert (np.asarray(flat).reshape(gold["idx"].shape) == gold["idx"]).mean() >= 0.99
+        assert ret["raised_%d" % r]
+    assert ret[0][1] == ret[1][1]

@@ -4,7 +4,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from lwm_b200.vqgan import VQGAN, init_params
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 16
-prec = sys.argv[2] if len(sys.argv) > 2 else "bf16x3"
+prec = sys.argv[2] if len(sys.argv) > 2 else "fp16x2"
 params = init_params(seed=0)
 x = (torch.rand(n, 256, 256, 3) * 2 - 1).cuda()
 tok = VQGAN(params, precision=prec)
