@@ -185,7 +185,7 @@ class Chunk:
 @dataclass
 class Group:
     chunks: List[Chunk] = field(default_factory=list)          # K/V chunks that must have arrived
-    launches: List[Tuple[int, int, int]] = field(default_factory=list)   # (q chunk idx, first global key row, rows)
+    launches: List[Tuple[int, int, int, int]] = field(default_factory=list)   # (q chunk idx, first global key row, rows, K/V owner)
 
 
 @dataclass
@@ -249,10 +249,13 @@ def make_peer_plan(world, rank, Sq, Sk, causal, layout="auto", fwd_group_chunks=
         remote += [c for c in need if c.owner == o]
 
     def launches_for(chunks):
+        # one launch per (q chunk, K/V owner): every operand carries its OWNER's fp16 scale (ring_peer.py), and the
+        # chunks of one owner are adjacent in position, so they merge into one range
         ls = []
         for qi, qc in enumerate(q_chunks):
-            for (p0, rows) in _merge_ranges([c for c in chunks if sees(qc, c)]):
-                ls.append((qi, p0, rows))
+            for o in sorted({c.owner for c in chunks}, key=lambda o_: [c.owner for c in chunks].index(o_)):
+                for (p0, rows) in _merge_ranges([c for c in chunks if c.owner == o and sees(qc, c)]):
+                    ls.append((qi, p0, rows, o))
         return ls
 
     # forward: local chunks first (their compute hides the first pulls), then the remote chunks in a few big groups
@@ -271,7 +274,7 @@ def make_peer_plan(world, rank, Sq, Sk, causal, layout="auto", fwd_group_chunks=
     order = (local[:1] + remote + local[1:]) if local else remote
     bwd_groups = []
     for c in order:
-        bwd_groups.append(Group([c], [(qi, c.pos0, c.length) for qi, qc in enumerate(q_chunks) if sees(qc, c)]))
+        bwd_groups.append(Group([c], [(qi, c.pos0, c.length, c.owner) for qi, qc in enumerate(q_chunks) if sees(qc, c)]))
     incoming = []
     for c in kv_chunks_of(world, rank, Sk, layout):
         for peer in range(world):

@@ -124,7 +124,7 @@ class _RingAttnFn(torch.autograd.Function):
         res = dict(q_chunks=list(saved[4:4 + n]), out_chunks=list(saved[4 + n:4 + 2 * n]),
                    lse_chunks=list(saved[4 + 2 * n:4 + 3 * n]))
         sc = list(saved[4 + 3 * n:4 + 3 * n + ctx.n_scales])
-        res["scales"] = tuple(sc) if sc else (None, None, None)
+        res["scales"] = tuple(sc) if sc else (None,) * (n + 2)
         group, rank, world = _resolve_group(ctx.axis_name)
         dq, dk, dv = ring_backward(res, k, v, dout.contiguous(), bias, seg, ctx.causal, group, rank, world,
                                    ctx.layout, ctx.precision)
@@ -347,6 +347,13 @@ class PeerOpsF16:
         _lib.call("lwm_attn_scale_from_absmax", _lib.ptr(table.view(-1)[col:]), table.shape[0], table.shape[1],
                   _lib.ptr(s), _lib.stream_ptr())
         return s
+
+    @staticmethod
+    def scale_of(x, out):
+        """out[0] = 2^(e-12), e the exponent of |x|max (the power-of-two scale of the fp16 operand copy of x)"""
+        bits = torch.zeros(1, dtype=torch.int32, device=x.device)
+        _lib.call("lwm_attn_absmax", _lib.ptr(x), _dt(x), x.numel(), _lib.ptr(bits), _lib.stream_ptr())
+        _lib.call("lwm_attn_scale_from_absmax", _lib.ptr(bits), 1, 1, _lib.ptr(out), _lib.stream_ptr())
 
     @staticmethod
     def stage(x, dst, scale):

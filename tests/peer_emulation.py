@@ -98,6 +98,10 @@ class EmuOps:
         e = torch.floor(torch.log2(m))
         return torch.pow(torch.tensor(2.0), e - 12).reshape(1)
 
+    def scale_of(self, x, out):
+        m = float(x.detach().abs().max())
+        out.fill_(1.0 if m == 0.0 else 2.0 ** (int(torch.floor(torch.log2(torch.tensor(m)))) - 12))
+
     def stage(self, x, dst, scale):
         dst.copy_(x.to(torch.float32) / (scale if scale is not None else 1.0))
 

@@ -119,7 +119,7 @@ def test_plan_properties():
             work = 0.0
             for g in p.bwd_groups:
                 c = g.chunks[0]
-                for (qi, p0, rows) in g.launches:
+                for (qi, p0, rows, _o) in g.launches:
                     work += 0.5 if p.q_chunks[qi].pos0 == p0 else 1.0
             assert work == 2.0 * P, (P, r, work)
             # every partial a rank sends has a landing slot at its owner, and vice versa

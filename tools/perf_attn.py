@@ -24,9 +24,13 @@ def main():
         B, H, D = 1, 32, 128
         q, k, v, do = [torch.randn(B, S, H, D, device="cuda").to(torch.bfloat16) for _ in range(4)]
         out = torch.empty_like(q)
+        fsc = bsc = None
+        if (sys.argv[3] if len(sys.argv) > 3 else "fp16") == "fp16":     # the default precision mode's kernels
+            (q, sq), (k, sk), (v, sv), (do16, sd) = [ra.to_f16(t) for t in (q, k, v, do)]
+            fsc, bsc = (sq, sk, sv), (sq, sk, sv, sd)
         lse = torch.empty(B, H, S, dtype=torch.float32, device="cuda")
         f_fwd = 4.0 * B * H * D * S * (S + 1) / 2
-        ms = time_fn(lambda: ra.fwd_step(q, k, v, out, lse, None, None, None, 0, 0, True, None, None, True, True))
+        ms = time_fn(lambda: ra.fwd_step(q, k, v, out, lse, None, None, None, 0, 0, True, None, None, True, True, scales=fsc))
         print("fwd  causal S=%6d: %8.3f ms  %7.1f TFLOP/s" % (S, ms, f_fwd / ms / 1e9))
         if which == "bwd":
             delta = torch.empty_like(lse)
@@ -34,8 +38,9 @@ def main():
             dk = torch.zeros_like(dq)
             dv = torch.zeros_like(dq)
             ra.bwd_prep(out, do, delta)
-            nl = ra.lse_for_bwd(lse)
-            ms = time_fn(lambda: ra.bwd_step(q, k, v, do, nl, delta, dq, dk, dv, 0, 0, True, None, None))
+            nl = ra.lse_for_bwd(lse, f16=bsc is not None)
+            dd = do16 if bsc is not None else do
+            ms = time_fn(lambda: ra.bwd_step(q, k, v, dd, nl, delta, dq, dk, dv, 0, 0, True, None, None, scales=bsc))
             print("bwd  causal S=%6d: %8.3f ms  %7.1f TFLOP/s" % (S, ms, 2.5 * f_fwd / ms / 1e9))
 
 
