@@ -122,6 +122,8 @@ int lwm_attn_bwd_step_f16(const void* q16, const void* k16, const void* v16, con
  * HOST array of device pointers. */
 #define LWM_REDUCE_MAX_SRCS 16
 int lwm_attn_absmax(const void* x, int dtype, long long n, unsigned* out_bits, void* stream);
+/* |x|max -> *scale_out = 2^(e-12) in one call (workspace: 4 bytes, zeroed here) */
+int lwm_attn_absmax_scale(const void* x, int dtype, long long n, unsigned* workspace, float* scale_out, void* stream);
 int lwm_attn_scale_from_absmax(const unsigned* bits, int n, int stride, float* scale_out, void* stream);
 int lwm_attn_to_f16_scaled(const void* x, int dtype, void* dst_f16, const float* scale, long long n, void* stream);
 int lwm_attn_bwd_prep_f16(const void* out, int out_dtype, const void* dout16, const float* scale_do, float* delta, int B,

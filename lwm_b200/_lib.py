@@ -27,6 +27,7 @@ _SIGNATURES = {
     "lwm_attn_bwd_step_f16": [c_void_p] * 13 + [c_int] * 5 + [c_ll, c_ll, c_int, c_void_p, c_ll, c_void_p, c_ll,
                                                              c_float, c_int, c_void_p],
     "lwm_attn_absmax": [c_void_p, c_int, c_ll, c_void_p, c_void_p],
+    "lwm_attn_absmax_scale": [c_void_p, c_int, c_ll, c_void_p, c_void_p, c_void_p],
     "lwm_attn_scale_from_absmax": [c_void_p, c_int, c_int, c_void_p, c_void_p],
     "lwm_attn_to_f16_scaled": [c_void_p, c_int, c_void_p, c_void_p, c_ll, c_void_p],
     "lwm_attn_bwd_prep_f16": [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],

@@ -320,6 +320,20 @@ extern "C" int lwm_attn_absmax(const void* x, int dtype, long long n, unsigned* 
   return lwm_check_launch("absmax kernel");
 }
 
+// |x|max -> power-of-two scale in one call: workspace (4 bytes) is zeroed, filled by the absmax kernel, and turned into
+// *scale_out = 2^(e-12). What the ring executor runs per shard before staging (every operand carries its owner's scale).
+extern "C" int lwm_attn_absmax_scale(const void* x, int dtype, long long n, unsigned* workspace, float* scale_out, void* stream) {
+  if (!x || !workspace || !scale_out || n <= 0 || n % 8 || (dtype != 0 && dtype != 1))
+    return lwm_fail(LWM_ERR_ARG, "attn_absmax_scale: bad arguments (n % 8 == 0)");
+  if (!lwm_check_device()) return LWM_ERR_DEVICE;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (cudaMemsetAsync(workspace, 0, 4, st) != cudaSuccess) return lwm_fail(LWM_ERR_CUDA, "attn_absmax_scale: memset failed");
+  if (dtype == 1) absmax_bf16_kernel<<<grid_for(n / 8, 256, 8), 256, 0, st>>>(reinterpret_cast<const uint4*>(x), n / 8, workspace);
+  else absmax_f32_kernel<<<grid_for(n / 4, 256, 8), 256, 0, st>>>(reinterpret_cast<const uint4*>(x), n / 4, workspace);
+  scale_from_absmax_kernel<<<1, 1, 0, st>>>(workspace, 1, 1, scale_out);
+  return lwm_check_launch("absmax_scale kernels");
+}
+
 extern "C" int lwm_attn_scale_from_absmax(const unsigned* bits, int n, int stride, float* scale_out, void* stream) {
   if (!bits || !scale_out || n <= 0 || stride <= 0) return lwm_fail(LWM_ERR_ARG, "attn_scale_from_absmax: bad arguments");
   if (!lwm_check_device()) return LWM_ERR_DEVICE;

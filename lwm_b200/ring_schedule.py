@@ -225,7 +225,18 @@ def _merge_ranges(chunks):
     return out
 
 
+_PLAN_CACHE = {}
+
+
 def make_peer_plan(world, rank, Sq, Sk, causal, layout="auto", fwd_group_chunks=4):
+    """cached: the plan is a pure function of its arguments and is asked for twice per layer and step"""
+    key = (world, rank, Sq, Sk, bool(causal), layout, fwd_group_chunks)
+    if key not in _PLAN_CACHE:
+        _PLAN_CACHE[key] = _make_peer_plan(*key)
+    return _PLAN_CACHE[key]
+
+
+def _make_peer_plan(world, rank, Sq, Sk, causal, layout, fwd_group_chunks):
     layout = choose_layout(world, Sq, Sk, causal, layout)
     q_chunks = compute_chunks(world, rank, Sq, layout)
     q_sends = []

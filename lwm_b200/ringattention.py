@@ -351,9 +351,9 @@ class PeerOpsF16:
     @staticmethod
     def scale_of(x, out):
         """out[0] = 2^(e-12), e the exponent of |x|max (the power-of-two scale of the fp16 operand copy of x)"""
-        bits = torch.zeros(1, dtype=torch.int32, device=x.device)
-        _lib.call("lwm_attn_absmax", _lib.ptr(x), _dt(x), x.numel(), _lib.ptr(bits), _lib.stream_ptr())
-        _lib.call("lwm_attn_scale_from_absmax", _lib.ptr(bits), 1, 1, _lib.ptr(out), _lib.stream_ptr())
+        bits = torch.empty(1, dtype=torch.int32, device=x.device)
+        st = _lib.stream_ptr()
+        _lib.call("lwm_attn_absmax_scale", _lib.ptr(x), _dt(x), x.numel(), _lib.ptr(bits), _lib.ptr(out), st)
 
     @staticmethod
     def stage(x, dst, scale):

@@ -20,10 +20,16 @@ def main():
     q, k, v, do = [syn.shard(n_, rank, Sl, H, D).to(dev) for n_ in ("q", "k", "v", "do")]
     kw = dict(axis_name="sp", blockwise_kwargs=dict(causal_block_size=1))
 
+    import time
+    host = {}
+
     def step():
         qq, kk, vv = [t.detach().requires_grad_(True) for t in (q, k, v)]
+        h0 = time.perf_counter()
         o = ra.ringattention(qq, kk, vv, None, None, **kw)
+        h1 = time.perf_counter()
         o.backward(do)
+        host["fwd_ms"], host["bwd_ms"] = (h1 - h0) * 1e3, (time.perf_counter() - h1) * 1e3
     for _ in range(3):
         step()
     tr = rp.CudaPeerTransport.get(dist.group.WORLD, dev)
@@ -41,7 +47,8 @@ def main():
     tr.trace = None
     total = t0.elapsed_time(t1)
     kern = sum(e - s for (lab, st, s, e) in spans if "kernel" in lab)
-    lines = ["rank %d: pass %.2f ms, tile kernels %.2f ms (%.1f %%)" % (rank, total, kern, 100 * kern / total)]
+    lines = ["rank %d: pass %.2f ms, tile kernels %.2f ms (%.1f %%); host enqueue fwd %.2f ms, bwd %.2f ms" % (
+        rank, total, kern, 100 * kern / total, host["fwd_ms"], host["bwd_ms"])]
     for (lab, st, s, e) in sorted(spans, key=lambda x: x[2]):
         lines.append("  %-5s %8.3f .. %8.3f  (%7.3f)  %s" % (st, s, e, e - s, lab))
     out = [None] * world
