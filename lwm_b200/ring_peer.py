@@ -372,7 +372,7 @@ class _Puller:
     """Enqueues the K/V pulls group by group, a couple of groups ahead of the compute loop: the first tile kernel is
     launched as soon as ITS operands are on their way instead of after the whole pass's transfer list was enqueued."""
 
-    def __init__(self, tr, lay, which, groups, KG, VG, gate, tag, lookahead=2):
+    def __init__(self, tr, lay, which, groups, KG, VG, gate, tag, lookahead=1):
         self.tr, self.lay, self.which, self.groups, self.KG, self.VG, self.gate = tr, lay, which, groups, KG, VG, gate
         self.tag, self.lookahead, self.events = tag, lookahead, []
 
@@ -399,6 +399,20 @@ def run_forward(plan, q, k, v, bias, seg, causal, ops, tr, want_f32=False):
     tr.ensure(lay.total)
     pid = tr.next_pass()
     which = pid & 1
+    # (result / carry buffers are allocated up front: nothing but enqueues stands between staging and the first kernel)
+    n_q = len(plan.q_chunks)
+    n_launch = [sum(1 for g in plan.fwd_groups for l in g.launches if l[0] == i) for i in range(n_q)]
+    lens = [qc.length for qc in plan.q_chunks]
+    out_chunks = [torch.empty((B, L, H, D), dtype=torch.bfloat16, device=dev) for L in lens]
+    need32 = want_f32 or ops.scaled     # fp16 mode keeps the un-rounded output as the backward's residual
+    out32 = [torch.empty((B, L, H, D), dtype=torch.float32, device=dev) if need32 else None for L in lens]
+    lse_chunks = [torch.empty((B, H, L), dtype=torch.float32, device=dev) for L in lens]
+    acc = [None] * n_q
+    for i in range(n_q):
+        if n_launch[i] > 1:
+            acc[i] = (torch.empty((B, lens[i], H, D), dtype=torch.float32, device=dev),
+                      torch.empty((B, H, lens[i]), dtype=torch.float32, device=dev),
+                      torch.empty((B, H, lens[i]), dtype=torch.float32, device=dev))
     tr.wait_event("pull", tr.record("main"))            # this set's previous consumers (pass pid-2) are done
     with _span(tr, "fwd stage q,k,v", "main"):
         KG, VG, QS, table = _stage_and_announce(tr, lay, which, pid, ops, k, v, q, (1, 2, 0))
@@ -415,19 +429,6 @@ def run_forward(plan, q, k, v, bias, seg, causal, ops, tr, want_f32=False):
     tr.wait_event("pull", ev_q)                         # the Q chunks first: the K/V stream must not share their bandwidth
     puller = _Puller(tr, lay, which, plan.fwd_groups, KG, VG, gate, "fwd")
 
-    n_q = len(q_chunks)
-    n_launch = [sum(1 for g in plan.fwd_groups for l in g.launches if l[0] == i) for i in range(n_q)]
-    out_chunks = [torch.empty((B, c.shape[1], H, D), dtype=torch.bfloat16, device=dev) for c in q_chunks]
-    need32 = want_f32 or ops.scaled     # fp16 mode keeps the un-rounded output as the backward's residual
-    out32 = [torch.empty((B, c.shape[1], H, D), dtype=torch.float32, device=dev) if need32 else None for c in q_chunks]
-    lse_chunks = [torch.empty((B, H, c.shape[1]), dtype=torch.float32, device=dev) for c in q_chunks]
-    acc = [None] * n_q
-    for i in range(n_q):
-        if n_launch[i] > 1:
-            L = q_chunks[i].shape[1]
-            acc[i] = (torch.empty((B, L, H, D), dtype=torch.float32, device=dev),
-                      torch.empty((B, H, L), dtype=torch.float32, device=dev),
-                      torch.empty((B, H, L), dtype=torch.float32, device=dev))
     done = [0] * n_q
     first_wait = True
     for gi, g in enumerate(plan.fwd_groups):
