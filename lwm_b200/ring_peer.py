@@ -243,6 +243,21 @@ def _pick(tr, name):
     return f(name) if f is not None else name
 
 
+def _pull_striped(tr, dst, peer, off):
+    """Pull the rows of `dst` ([rows, ...], contiguous) from `peer`'s heap at byte offset `off`, striped over the members
+    of the 'pull' fan-out: every member carries a slice of EVERY transfer, in issue order — transfers complete in the
+    order they are needed at the aggregate bandwidth, with no cross-stream dependency between them."""
+    f = getattr(tr, "_members", None)
+    members = f("pull") if f is not None else ["pull"]
+    rows = dst.shape[0]
+    n = min(len(members), rows)
+    row_bytes = dst[0].numel() * dst.element_size()
+    for i in range(n):
+        a, b = rows * i // n, rows * (i + 1) // n
+        if b > a:
+            tr.pull(dst[a:b], peer, off + a * row_bytes, members[i])
+
+
 def _span(tr, label, stream):
     f = getattr(tr, "span", None)
     return f(label, stream) if f is not None else _NoSpan()
@@ -324,23 +339,23 @@ def _gather_q_chunks(tr, lay, which, plan, QS, gate, ops):
         else:
             buf = torch.empty((B, qc.length) + tuple(QS.shape[2:]), dtype=QS.dtype, device=QS.device)
             gate(qc.owner, "pull")
-            st = _pick(tr, "pull")
             for b in range(B):
-                tr.pull(buf[b], qc.owner, lay.q_row_off("qs", which, b, qc.start, lay.isz), st)
+                _pull_striped(tr, buf[b], qc.owner, lay.q_row_off("qs", which, b, qc.start, lay.isz))
             chunks.append(buf)
     return chunks
 
 
 def _pull_group(tr, lay, which, group, KG, VG, gate):
     B = KG.shape[0]
+    if all(c.owner == tr.rank for c in group.chunks):
+        return []                       # local rows are already in place: nothing to wait for
     for c in group.chunks:
         if c.owner == tr.rank:
             continue
         gate(c.owner, "pull")
         for b in range(B):
             for region, arr in (("kg", KG), ("vg", VG)):
-                tr.pull(arr[b, c.pos0:c.pos0 + c.length], c.owner, lay.kv_row_off(region, which, b, c.pos0),
-                        _pick(tr, "pull"))
+                _pull_striped(tr, arr[b, c.pos0:c.pos0 + c.length], c.owner, lay.kv_row_off(region, which, b, c.pos0))
     return tr.record("pull")
 
 
@@ -413,7 +428,6 @@ def run_forward(plan, q, k, v, bias, seg, causal, ops, tr, want_f32=False):
             acc[i] = (torch.empty((B, lens[i], H, D), dtype=torch.float32, device=dev),
                       torch.empty((B, H, lens[i]), dtype=torch.float32, device=dev),
                       torch.empty((B, H, lens[i]), dtype=torch.float32, device=dev))
-    tr.wait_event("pull", tr.record("main"))            # this set's previous consumers (pass pid-2) are done
     with _span(tr, "fwd stage q,k,v", "main"):
         KG, VG, QS, table = _stage_and_announce(tr, lay, which, pid, ops, k, v, q, (1, 2, 0))
     # scale rows [sq, sk, sv, sdo] of every owner, local copy (mine straight from the heap row I just wrote)
@@ -421,12 +435,11 @@ def run_forward(plan, q, k, v, bias, seg, causal, ops, tr, want_f32=False):
     if ops.scaled:
         scales = torch.empty((tr.world, 4), dtype=torch.float32, device=dev)
         scales[r].copy_(table[r])
-    tr.wait_event("pull", tr.record("main"))
+    tr.wait_event("pull", tr.record("main"))            # after everything that still reads this set (pass pid-2) and my staging
     gate = _OwnerGate(tr, pid, lay, which, scales)
     with _span(tr, "fwd pull q chunks", "pull"):
         q_chunks = _gather_q_chunks(tr, lay, which, plan, QS, gate, ops)
-    ev_q = tr.record("pull")
-    tr.wait_event("pull", ev_q)                         # the Q chunks first: the K/V stream must not share their bandwidth
+    ev_q = tr.record("pull")        # (every pull member carries its slice of the Q chunks before any K/V slice)
     puller = _Puller(tr, lay, which, plan.fwd_groups, KG, VG, gate, "fwd")
 
     done = [0] * n_q
@@ -486,8 +499,6 @@ def run_backward(plan, res, k, v, dout, bias, seg, causal, ops, tr, want_f32=Fal
     tr.ensure(lay.total)
     pid = tr.next_pass()
     which = pid & 1
-    tr.wait_event("pull", tr.record("main"))
-    tr.wait_event("push", tr.record("main"))
     q_chunks, out_chunks, lse_chunks = res["q_chunks"], res["out_chunks"], res["lse_chunks"]
     n_q = len(q_chunks)
     q_scales, (sk_own, sv_own) = res["scales"][:n_q], res["scales"][n_q:n_q + 2]
@@ -503,7 +514,6 @@ def run_backward(plan, res, k, v, dout, bias, seg, causal, ops, tr, want_f32=Fal
     with _span(tr, "bwd pull dO chunks", "pull"):
         do_chunks = _gather_q_chunks(tr, lay, which, plan, DS, gate, ops)
     ev_q = tr.record("pull")
-    tr.wait_event("pull", ev_q)
     puller = _Puller(tr, lay, which, plan.bwd_groups, KG, VG, gate, "bwd")
     puller.event(0)
 
