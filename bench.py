@@ -366,8 +366,16 @@ def main():
     parity = None
     if not args.no_parity:
         from lwm_b200.selftest import sampled_parity
-        pe = sampled_parity(S, H, [0, H - 1], lambda a, b, c: ra.ringattention(a, b, c, None, None, **kwargs), dev, rank,
-                            world, 1234, shards=dict(q=q, k=k, v=v, do=do))
+        # (a failure here is reported in the line, it must not take the measurement down with it; every rank takes the
+        # same branch: an exception on one rank would leave the others in the all_reduce below)
+        try:
+            pe = sampled_parity(S, H, [0, H - 1], lambda a, b, c: ra.ringattention(a, b, c, None, None, **kwargs), dev,
+                                rank, world, 1234, shards=dict(q=q, k=k, v=v, do=do))
+        except Exception as e:      # noqa: BLE001
+            if world > 1:
+                raise               # a multi-rank failure cannot be papered over: the other ranks are inside the op
+            pe = {"out": 9.0, "dq": 9.0, "dk": 9.0, "dv": 9.0, "dq_unsampled_abs": 9.0, "rows": 0, "keys": 0}
+            print("parity check failed: %s: %s" % (type(e).__name__, str(e)[:300]), file=sys.stderr)
         worst = max(pe[n_] for n_ in ("out", "dq", "dk", "dv"))
         tp = torch.tensor([pe["out"], pe["dq"], pe["dk"], pe["dv"], pe["dq_unsampled_abs"], worst], device=dev)
         tn = torch.tensor([float(pe["rows"]), float(pe["keys"])], device=dev)
@@ -439,13 +447,13 @@ def main():
         fl_bwd = 2.5 * f_fwd(S)
         ach = fl_bwd / (kern_ms["bwd"] * 1e-3) / 1e12
         traffic = None   # dram__bytes_read+write of one attn_bwd_kernel launch at S=131072 (ncu --set full capture)
-        tp = os.path.join(ROOT, "profiles", "ncu_attn_128k_r01.json")
+        tp = os.path.join(ROOT, "profiles", "ncu_attn_128k_r02.json")
         if S == S_TOTAL and os.path.exists(tp):
             traffic = json.load(open(tp))["attn_bwd_kernel"]["dram_total_bytes"]
         roof = {"bound": "tensor", "kernel": "attn_bwd_kernel<%s>" % ("fp16 operands" if prec == "fp16" else "bf16 operands"),
                 "achieved": ach, "peak": peaks["sustained"],
                 "unit": "TFLOP/s", "frac": ach / peaks["sustained"], "traffic": traffic,
-                "traffic_note": "bytes per launch from profiles/ncu_attn_128k_r01.json; algorithmic minimum ~17 GB "
+                "traffic_note": "bytes per launch from profiles/ncu_attn_128k_r02.json; algorithmic minimum ~17 GB "
                                 "(q,k,v,dout once + dq/dk/dv fp32 read-modify-write); tensor-bound, HBM < 2 % busy",
                 "peak_source": peaks["source"] + " bf16_tflops_sustained (kernel timed inside a long step); burst=%.1f"
                 % peaks["burst"],
@@ -526,7 +534,10 @@ def main():
     # ---- VQGAN encode: 16 frames of 256x256 (replicas: every rank encodes its own clip, no collective)
     vq = None
     if not args.no_vqgan:
-        vq = bench_vqgan(dev, peaks, world, rank, with_cpu=not args.no_cpu_baseline)
+        try:
+            vq = bench_vqgan(dev, peaks, world, rank, with_cpu=not args.no_cpu_baseline)
+        except Exception as e:      # noqa: BLE001  (the attention line must still be printed)
+            vq = {"error": "%s: %s" % (type(e).__name__, str(e)[:300])}
 
     if rank == 0:
         total_flops = 3.5 * f_fwd(S)
@@ -556,6 +567,7 @@ def main():
         if vq:
             line["vqgan"] = vq
         if not args.no_cpu_baseline:
+          try:
             cores = min(len(os.sched_getaffinity(0)), 32)   # more threads only add contention at this size
             torch.set_num_threads(cores)
             cpu_sample_step(1024, 1024, 4, chunk=512)       # warm the thread pool
@@ -565,6 +577,8 @@ def main():
                 "gflops": fl / dt / 1e9,
                 "sample": "oracle blockwise fwd+bwd (torch CPU fp32) of one full layer at S=4096 (BASELINE configs[0]; "
                           "32 heads, causal); %.1f s of CPU work; tokens/s = 4096 / (32 layers * t)" % dt}
+          except Exception as e:      # noqa: BLE001
+            line["cpu_baseline"] = {"error": "%s: %s" % (type(e).__name__, str(e)[:200])}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
