@@ -478,14 +478,22 @@ def main():
         hdk.copy_(kd.grad, non_blocking=True)
         hdv.copy_(vd.grad, non_blocking=True)
 
+    # the caller's persistent device staging buffers and copy streams (allocated once, outside the timed region)
+    e2e_state = {}
+
+    def e2e_setup():
+        e2e_state["up"], e2e_state["down"] = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        e2e_state["dbuf"] = [[torch.empty_like(q) for _ in range(4)] for _ in range(2)]
+
     def e2e_pipelined(n):
         """Same copies per step, but double-buffered: two copy streams move step i+1's inputs up and step i-1's results
-        down while step i's kernels run (what a caller streaming layers / micro-batches through the op would do)."""
+        down while step i's kernels run (what a caller streaming layers / micro-batches through the op would do).
+        Results stay referenced until the main stream has waited for their download, so the allocator never hands a
+        block that a copy is still reading to the next step (no record_stream, no allocation churn)."""
         main = torch.cuda.current_stream(dev)
-        up, down = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
-        dbuf = [[torch.empty_like(q) for _ in range(4)] for _ in range(2)]
+        up, down, dbuf = e2e_state["up"], e2e_state["down"], e2e_state["dbuf"]
         up.wait_stream(main)
-        up_done, free = [None, None], [None, None]
+        up_done, free, down_done, keep = [None, None], [None, None], [None, None], [None, None]
 
         def upload(slot):
             with torch.cuda.stream(up):
@@ -500,22 +508,30 @@ def main():
             if i + 1 < n:
                 upload(1 - s)
             main.wait_event(up_done[s])
+            if down_done[s] is not None:        # the results of step i-2 have left the device: their memory may be reused
+                main.wait_event(down_done[s])
+                keep[s] = None
             qd, kd, vd = [t.detach().requires_grad_(True) for t in dbuf[s][:3]]
             o = ra.ringattention(qd, kd, vd, None, None, **kwargs)
             o.backward(dbuf[s][3])
             free[s] = main.record_event()
+            keep[s] = (o, qd, kd, vd)
             with torch.cuda.stream(down):
                 down.wait_event(free[s])
                 for dst, src in ((hout, o.detach()), (hdq, qd.grad), (hdk, kd.grad), (hdv, vd.grad)):
                     dst.copy_(src, non_blocking=True)
-                    src.record_stream(down)
+                down_done[s] = down.record_event()
         main.wait_stream(down)
+        keep[0] = keep[1] = None
 
     e2e_step()
+    n_e2e = max(3, min(K, 6))
+    if not args.e2e_serial:
+        e2e_setup()
+        e2e_pipelined(2)            # warm-up of the pipelined path (untimed)
     barrier()
     a, b2 = ev(), ev()
     a.record()
-    n_e2e = max(3, min(K, 6))
     if not args.e2e_serial:
         e2e_pipelined(n_e2e)
     else:

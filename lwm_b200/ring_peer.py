@@ -85,6 +85,10 @@ class Layout:
 # ------------------------------------------------------------------------------------------------
 # CUDA transport over the C-ABI ring context
 # ------------------------------------------------------------------------------------------------
+class PeerTransportUnavailable(RuntimeError):
+    """raised by every rank of the group together when the peer-memory heaps cannot be set up on this box"""
+
+
 class _RawCuda:
     def __init__(self, addr, nbytes):
         self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (addr, False), "version": 2}
@@ -125,15 +129,32 @@ class CudaPeerTransport:
             self.ctx = None
         want = int(nbytes * 1.05) + (1 << 20)
         lib = _lib.load()
-        ctx = ctypes.c_void_p()
-        _lib.call("lwm_ring_ctx_create", self.rank, self.world, want, self.signal_mode, ctypes.byref(ctx))
+        # Bootstrap: every step that can fail on a box (heap allocation, IPC export / mapping of the peers) is tried by all
+        # ranks, and the ranks AGREE on the outcome before anybody relies on it: if one rank cannot map its peers, all of
+        # them raise PeerTransportUnavailable together (ringattention.py then switches the process group to the two-sided
+        # NCCL executor, loudly) instead of one rank raising while the others wait for its flags forever.
+        ctx, err = ctypes.c_void_p(), None
         handle = (ctypes.c_ubyte * 64)()
-        _lib.call("lwm_ring_ctx_get_handle", ctx, handle)
+        try:
+            _lib.call("lwm_ring_ctx_create", self.rank, self.world, want, self.signal_mode, ctypes.byref(ctx))
+            _lib.call("lwm_ring_ctx_get_handle", ctx, handle)
+        except _lib.LwmError as e:
+            err = str(e)
         mine = torch.tensor(list(handle), dtype=torch.uint8, device=self.device)
         allh = torch.empty(self.world * 64, dtype=torch.uint8, device=self.device)
         dist.all_gather_into_tensor(allh, mine, group=self.group)
-        buf = (ctypes.c_ubyte * (self.world * 64))(*allh.cpu().tolist())
-        _lib.call("lwm_ring_ctx_open_peers", ctx, buf)
+        if err is None:
+            try:
+                buf = (ctypes.c_ubyte * (self.world * 64))(*allh.cpu().tolist())
+                _lib.call("lwm_ring_ctx_open_peers", ctx, buf)
+            except _lib.LwmError as e:
+                err = str(e)
+        ok = torch.tensor([0 if err else 1], dtype=torch.int32, device=self.device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)
+        if int(ok.item()) == 0:
+            if ctx.value:
+                _lib.call("lwm_ring_ctx_destroy", ctx)
+            raise PeerTransportUnavailable(err or "a peer rank could not set up its peer-memory heap")
         self.ctx, self.capacity, self.pass_id = ctx, want, 0
         self.heap_addr = [int(lib.lwm_ring_ctx_heap(ctx, p)) for p in range(self.world)]
         self.own = torch.as_tensor(_RawCuda(self.heap_addr[self.rank], want), device=self.device)

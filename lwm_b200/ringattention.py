@@ -168,7 +168,7 @@ def ringattention(q, k, v, attn_bias=None, segment_ids=None, *, axis_name="sp", 
         raise TypeError("ringattention: q, k, v must all be bfloat16 or all float32 (fp32 logits and accumulation "
                         "are internal)")
     group, rank, world = _resolve_group(axis_name)
-    native_f32 = in_dtype == torch.float32 and precision == "fp16" and (world == 1 or _transport() == "peer")
+    native_f32 = in_dtype == torch.float32 and precision == "fp16" and (world == 1 or _transport(group) == "peer")
     if in_dtype == torch.float32 and not native_f32:
         # bf16 operand mode / NCCL transport: fp32 callers go through one rounding of q/k/v to bf16 (2^-9 relative)
         q, k, v = q.to(torch.bfloat16), k.to(torch.bfloat16), v.to(torch.bfloat16)
@@ -416,13 +416,34 @@ class PeerOpsBf16(PeerOpsF16):
         bwd_step(q, k, v, dout, lse, delta, dq_acc, dk_acc, dv_acc, q_pos0, k_pos0, causal, bias, seg, init=init)
 
 
-def _transport():
+_PEER_BROKEN = {}      # process group id -> reason: the peer-memory heaps could not be set up for this group
+
+
+def _transport(group=None):
     """'peer' (default): copy-engine pulls/puts over peer-mapped heaps (ring_peer.py). 'nccl': the two-sided
-    send/recv executor (ring_exec.py) — kept as the portable alternative and for the gloo CPU tests."""
+    send/recv executor (ring_exec.py) — the portable alternative (and what the gloo CPU tests drive); also what a group
+    is switched to, with a warning, when all its ranks agree that the peer heaps cannot be mapped on this box."""
     t = os.environ.get("LWM_RING_TRANSPORT", "peer")
     if t not in ("nccl", "peer"):
         raise ValueError("LWM_RING_TRANSPORT must be 'peer' or 'nccl'")
+    if t == "peer" and (id(group) if group is not None else 0) in _PEER_BROKEN:
+        return "nccl"
     return t
+
+
+def _peer_transport(group, device, nbytes_hint=0):
+    """the group's peer transport, or None (after a collective, loud switch to NCCL) when it cannot be set up"""
+    import warnings
+    try:
+        tr = rp.CudaPeerTransport.get(group, device)
+        if nbytes_hint:
+            tr.ensure(nbytes_hint)
+        return tr
+    except rp.PeerTransportUnavailable as e:
+        _PEER_BROKEN[id(group) if group is not None else 0] = str(e)
+        warnings.warn("lwm_b200: peer-memory ring transport unavailable (%s): this process group now uses the two-sided "
+                      "NCCL executor (LWM_RING_TRANSPORT=nccl)" % e)
+        return None
 
 
 def _ops_for(precision):
@@ -469,10 +490,16 @@ def ring_forward(q, k, v, bias, seg, causal, group, rank, world, layout="auto", 
         res = dict(q_chunks=[q16], out_chunks=[out32 if ops.scaled else out], lse_chunks=[lse], scales=(sq, sk, sv))
         return (out32 if want_f32 else out), res
     lay = rs.choose_layout(world, Sq, k.shape[1], causal, layout)
-    if _transport() == "peer":
+    if _transport(group) == "peer":
         plan = rs.make_peer_plan(world, rank, Sq, k.shape[1], causal, lay)
-        return rp.run_forward(plan, q, k, v, bias, seg, causal, _peer_ops(precision),
-                              rp.CudaPeerTransport.get(group, q.device), want_f32)
+        pops = _peer_ops(precision)
+        tr = _peer_transport(group, q.device, rp._layout_for(plan, q.shape, k.shape[1], pops).total)
+        if tr is not None:
+            return rp.run_forward(plan, q, k, v, bias, seg, causal, pops, tr, want_f32)
+        if want_f32:        # the NCCL executor takes bf16 operands (documented in ringattention())
+            out, res = ring_forward(q.to(torch.bfloat16), k.to(torch.bfloat16), v.to(torch.bfloat16), bias, seg, causal,
+                                    group, rank, world, layout, precision)
+            return out.float(), res
     ops = _ops_for(precision)
     plan = rs.make_plan(world, rank, Sq, k.shape[1], causal, lay, n_sub_first=rs.auto_sub(world, k.shape[1], lay))
     out, res = rx.run_forward(plan, q, k, v, bias, seg, causal, group, ops)
@@ -506,10 +533,14 @@ def ring_backward(res, k, v, dout, bias, seg, causal, group, rank, world, layout
         cast_f32_to_bf16(dv_acc, dv)
         return dq, dk, dv
     lay = rs.choose_layout(world, dout.shape[1], Sk, causal, layout)
-    if _transport() == "peer":
+    if _transport(group) == "peer":
         plan = rs.make_peer_plan(world, rank, dout.shape[1], Sk, causal, lay)
         return rp.run_backward(plan, res, k, v, dout, bias, seg, causal, _peer_ops(precision),
                                rp.CudaPeerTransport.get(group, dev), want_f32)
+    if want_f32:            # forward fell back to the NCCL executor: bf16 operands in, fp32 gradients out
+        dq, dk, dv = ring_backward(res, k.to(torch.bfloat16), v.to(torch.bfloat16), dout.to(torch.bfloat16), bias, seg,
+                                   causal, group, rank, world, layout, precision)
+        return dq.float(), dk.float(), dv.float()
     ops = _ops_for(precision)
     n_sub = rs.auto_sub(world, Sk, lay)
     plan = rs.make_plan(world, rank, dout.shape[1], Sk, causal, lay, n_sub_first=n_sub, n_sub_last=n_sub)
