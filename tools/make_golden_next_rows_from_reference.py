@@ -80,3 +80,19 @@ def make_vision_tokens():
 if __name__ == "__main__":
     make_rope()
     make_vision_tokens()
+
+
+def make_process_frame_fixture(path="tests/golden/process_frame_reference.npz"):
+    """tests/golden/process_frame_reference.npz: outputs of the reference's own `Sampler._process_frame`
+    (lwm/vision_chat.py:59-74), source text extracted with ast and executed, on the seeded images of
+    tests/test_next_rows2_cpu.py::_images at size 64."""
+    import ast
+    import sys
+    import numpy as np
+    sys.path.insert(0, "tests")
+    from test_next_rows2_cpu import _images
+    src = open("/root/reference/lwm/vision_chat.py").read()
+    fn = next(n for n in ast.walk(ast.parse(src)) if isinstance(n, ast.FunctionDef) and n.name == "_process_frame")
+    ns = {"np": np}
+    exec("def _process_frame" + ast.get_source_segment(src, fn).split("def _process_frame", 1)[1], ns)
+    np.savez_compressed(path, **{"frame_%d" % i: ns["_process_frame"](None, im, 64) for i, im in enumerate(_images())})
