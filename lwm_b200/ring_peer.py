@@ -356,7 +356,9 @@ def _gather_q_chunks(tr, lay, which, plan, QS, gate, ops):
     chunks = []
     for qc in plan.q_chunks:
         if qc.owner == tr.rank:
-            chunks.append(QS[:, qc.start:qc.start + qc.length])
+            c = QS[:, qc.start:qc.start + qc.length]
+            # (B > 1: a row slice of the stage is strided over the batch; the step functions take contiguous tensors)
+            chunks.append(c if c.is_contiguous() else c.contiguous())
         else:
             buf = torch.empty((B, qc.length) + tuple(QS.shape[2:]), dtype=QS.dtype, device=QS.device)
             gate(qc.owner, "pull")
