@@ -194,6 +194,46 @@ int lwm_ring_signal(lwm_ring_ctx* ctx, int peer, int flag, unsigned value, void*
 int lwm_ring_wait(lwm_ring_ctx* ctx, int flag, unsigned value, void* stream);
 int lwm_ring_ctx_destroy(lwm_ring_ctx* ctx);
 
+/* The schedule and the heap layout of the peer-memory ring as pure functions (host-only; no device is touched), so that
+ * a host in any language can drive the lwm_ring_* primitives above. Same results as lwm_b200/ring_schedule.py::
+ * make_peer_plan and lwm_b200/ring_peer.py::Layout (tests/test_ring_plan_native_cpu.py compares them field by field).
+ * lwm_ring_plan: rank `rank` of `world`, per-rank shard lengths Sq / Sk, causal flag; zigzag = 1 selects the
+ *   load-balanced work assignment (rank r computes query half-chunks r and 2P-1-r; needs Sq == Sk, Sq % 256 == 0), 0 the
+ *   reference's (every rank its own rows). q[]: query chunks this rank computes (owner = rank whose shard holds the rows);
+ *   q_sends[]: rows of MY shard that a peer computes (it pulls them from my stage and puts the results back);
+ *   fwd/bwd groups: K/V chunks to have pulled before the group's launches (group g = chunks
+ *   [first_chunk[g], first_chunk[g+1]), launches [first_launch[g], first_launch[g+1])); a launch = query chunk q_chunk
+ *   against `rows` keys starting at global key row key_row0, all staged by `owner`; incoming[]: dK/dV partials that
+ *   will land in my heap, slot = chunk_index * world + peer; own_computed[]: my chunk indices I compute on myself.
+ * lwm_ring_layout: byte offsets of the regions inside one set (scales table [world][4] fp32, position-ordered K and V
+ *   arrays [B, world*Sk, H, D], Q/dO stage [B,Sq,H,D], 4-byte and 2-byte landing areas for O/dQ rows, dK/dV landing
+ *   slots: slot s = lp + (2*s + {0: dK, 1: dV}) * slot_bytes); set 1 starts at set_bytes. */
+#define LWM_RING_MAX_CHUNKS 32
+#define LWM_RING_MAX_LAUNCHES 128
+typedef struct { int owner, index; long long start, length, pos0; } lwm_ring_chunk;
+typedef struct { int q_chunk, owner; long long key_row0, rows; } lwm_ring_launch;
+typedef struct {
+  int world, rank, zigzag, chunks_per_rank;
+  int n_q; lwm_ring_chunk q[2];
+  int n_q_sends; struct { long long start, length; int peer; } q_sends[LWM_RING_MAX_CHUNKS];
+  int n_fwd_groups, n_fwd_chunks, n_fwd_launches;
+  int fwd_group_first_chunk[LWM_RING_MAX_CHUNKS + 1], fwd_group_first_launch[LWM_RING_MAX_CHUNKS + 1];
+  lwm_ring_chunk fwd_chunks[LWM_RING_MAX_CHUNKS]; lwm_ring_launch fwd_launches[LWM_RING_MAX_LAUNCHES];
+  int n_bwd_groups, n_bwd_chunks, n_bwd_launches;
+  int bwd_group_first_chunk[LWM_RING_MAX_CHUNKS + 1], bwd_group_first_launch[LWM_RING_MAX_CHUNKS + 1];
+  lwm_ring_chunk bwd_chunks[LWM_RING_MAX_CHUNKS]; lwm_ring_launch bwd_launches[LWM_RING_MAX_LAUNCHES];
+  int n_incoming; struct { int chunk_index, peer; } incoming[LWM_RING_MAX_CHUNKS];
+  int n_own; int own_computed[2];
+} lwm_ring_plan_t;
+typedef struct {
+  long long scales, kg, vg, qs, lq4, lq2, lp, slot_bytes, set_bytes, total, chunk_rows;
+  int n_slots;
+} lwm_ring_layout_t;
+int lwm_ring_plan(int world, int rank, long long Sq, long long Sk, int causal, int zigzag, int fwd_group_chunks,
+                  lwm_ring_plan_t* out);
+int lwm_ring_layout(int B, long long Sq, long long Sk, int H, int D, int world, int chunks_per_rank, int op_itemsize,
+                    lwm_ring_layout_t* out);
+
 /* ---------------------------------------------------------------------------------------------
  * VQGAN tokenizer (lwm/vqgan.py:105-351). Activations are NHWC fp32 (flax layout and dtype).
  *

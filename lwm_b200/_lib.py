@@ -39,6 +39,8 @@ _SIGNATURES = {
     "lwm_ring_signal": [c_void_p, c_int, c_int, ctypes.c_uint, c_void_p],
     "lwm_ring_wait": [c_void_p, c_int, ctypes.c_uint, c_void_p],
     "lwm_ring_ctx_destroy": [c_void_p],
+    "lwm_ring_plan": [c_int, c_int, c_ll, c_ll, c_int, c_int, c_int, c_void_p],
+    "lwm_ring_layout": [c_int, c_ll, c_ll, c_int, c_int, c_int, c_int, c_int, c_void_p],
     "lwm_attn_decode_partial": [c_void_p] * 7 + [c_int] * 5 + [c_ll, c_ll, c_ll, c_int, c_float, c_void_p],
     "lwm_attn_decode_merge": [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_ll, c_void_p],
     "lwm_cast_f32_to_bf16": [c_void_p, c_void_p, c_ll, c_void_p],
