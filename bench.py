@@ -140,7 +140,7 @@ def run_reference_arm(args, rank):
     import torch
     cores = min(len(os.sched_getaffinity(0)), 32)
     torch.set_num_threads(cores)
-    rows, heads = 4096, 2        # a fixed sample of the 128K problem: 1.9e12 FLOP per step (a few seconds on 32 cores)
+    rows, heads = 2048, 2        # a fixed sample of the 128K problem: 9.5e11 FLOP per step (~4 s on the box's 32 cores)
     times, flops = [], 0.0
     for i in range(args.warmup + args.steps):
         dt, flops = cpu_sample_step(S_TOTAL, rows, heads)
