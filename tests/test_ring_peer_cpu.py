@@ -133,3 +133,18 @@ def test_plan_properties():
             f = sorted((c.owner, c.index) for g in p.fwd_groups for c in g.chunks)
             b = sorted((c.owner, c.index) for g in p.bwd_groups for c in g.chunks)
             assert f == b
+
+
+def test_flag_ranges_do_not_collide():
+    """STAGED[rank], RES[rank] and PART[slot] live in one flag page: their index ranges are disjoint up to the largest
+    supported ring (16 ranks, 2 chunks per rank) and stay inside the page"""
+    from lwm_b200 import ring_peer as rp, ring_schedule as rs
+    world = 16
+    staged = set(range(rp.FLAG_STAGED, rp.FLAG_STAGED + world))
+    res = set(range(rp.FLAG_RES, rp.FLAG_RES + world))
+    plan = rs.make_peer_plan(world, 0, 1024, 1024, True, "zigzag")
+    part = {rp.FLAG_PART + plan.slot(ci, peer) for ci in range(plan.chunks_per_rank) for peer in range(world)}
+    assert not (staged & res) and not (staged & part) and not (res & part)
+    assert max(part) < 65536 // 4
+    lay = rp.Layout(1, 1024, 1024, 32, 128, world, 2, 2)
+    assert lay.n_slots == max(plan.slot(ci, peer) for ci in range(2) for peer in range(world)) + 1
