@@ -35,7 +35,6 @@ import torch
 import torch.distributed as dist
 
 from . import _lib
-from . import ring_schedule as rs
 
 FLAG_STAGED, FLAG_RES, FLAG_PART = 16, 32, 64
 _ALIGN = 256

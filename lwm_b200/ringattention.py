@@ -17,7 +17,6 @@ There is no fallback: without the library / an sm_100 GPU the op raises.
 """
 import math
 import os
-from typing import Optional
 
 import torch
 import torch.distributed as dist
